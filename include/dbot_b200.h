@@ -1,0 +1,128 @@
+/*
+ * include/dbot_b200.h -- C-ABI of libdbot_b200.so, the B200 (sm_100a) depth
+ * observation model for the dbot / dbot_ros particle tracker.
+ *
+ * Drop-in boundary.  In the reference the sensor is
+ * obtained at
+ *     ref:source/dbot_ros/tracker/particle_tracker_node.cpp:164-203
+ *     ref:source/dbot_ros/tracker/object_tracker_service_node.cpp:136-175
+ * (`dbot::RbSensorBuilder<State>(object_model, camera_data, params)`), where
+ * `params.use_gpu` (ref:config/particle_tracker.yaml:3) selects dbot's
+ * OpenGL+CUDA `KinectImageModelGPU`.  This library replaces that evaluator:
+ * each entry point below names the `dbot::RbSensor<State>` member (dbot
+ * model/rb_sensor.h, un-vendored) it stands in for.  INTEGRATION.md shows the
+ * C++ adapter a dbot maintainer would add.
+ *
+ * Conventions: plain C types only; caller owns every host buffer; the library
+ * owns all device memory and its CUDA stream; every call returns 0 on
+ * success, <0 for argument errors, >0 for a CUDA error code; text through
+ * dbot_b200_last_error() (thread-local).  One caller at a time per handle
+ * (the tracker serialises track() -- ref:source/dbot_ros/object_tracker_ros.hpp:111-125).
+ * There is no CPU fallback: without a CUDA device create() fails.
+ */
+#ifndef DBOT_B200_H
+#define DBOT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBOT_B200_ABI_VERSION 1
+#define DBOT_B200_MAX_OBJECTS 8
+
+typedef struct dbot_b200_sensor dbot_b200_sensor; /* opaque */
+
+/* Mirrors dbot::RbSensorBuilder<State>::Parameters + CameraData + ObjectModel, i.e.
+ * everything ref:source/dbot_ros/tracker/particle_tracker_node.cpp:84-203 hands to the builder. */
+typedef struct
+{
+    int32_t rows, cols;   /* resolution after downsampling
+                             (ref:source/dbot_ros/util/ros_interface.h:155-156) */
+    double K[9];          /* camera matrix, row-major, rows 0-1 already divided by the
+                             downsampling factor (ref:source/dbot_ros/util/ros_camera_data_provider.cpp:72);
+                             K[3]=K[6]=K[7]=0 and K[8]=1 required */
+    int32_t max_particles; /* = sample_count (ref:config/particle_tracker.yaml:7,11) */
+    int32_t n_objects;     /* <= DBOT_B200_MAX_OBJECTS */
+    const float* const* vertices;    /* [n_objects] -> float[3*n_vertices[o]], object frame
+                                        (centred when center_object_frame,
+                                        ref:source/dbot_ros/tracker/particle_tracker_node.cpp:92-97) */
+    const int32_t* n_vertices;
+    const int32_t* const* triangles; /* [n_objects] -> int32[3*n_triangles[o]] */
+    const int32_t* n_triangles;
+    double tail_weight, model_sigma, sigma_factor; /* ref:config/particle_tracker.yaml:47-49 */
+    double half_life_depth, max_depth;             /* dbot KinectPixelModel defaults: 1.0, 6.0 */
+    double p_occluded_visible, p_occluded_occluded,
+        initial_occlusion_prob;                    /* ref:config/particle_tracker.yaml:41-43 */
+    double delta_time;   /* ref:source/dbot_ros/tracker/particle_tracker_node.cpp:189 (1/30) */
+    int32_t device_id;   /* CUDA device ordinal of this handle (one handle per GPU) */
+    int32_t occlusion_mode; /* 0 = dense eager: one full-frame fp32 occlusion image per
+                               particle, propagated on every update (semantics of dbot's GPU
+                               evaluator).  Other values are reserved. */
+} dbot_b200_config;
+
+/* RbSensorBuilder<State>::build() with use_gpu == true */
+int dbot_b200_create(const dbot_b200_config* cfg, dbot_b200_sensor** out);
+int dbot_b200_destroy(dbot_b200_sensor* s);
+
+/* RbSensor<State>::reset(): one occlusion slot at initial_occlusion_prob, observation time 0 */
+int dbot_b200_reset(dbot_b200_sensor* s);
+
+/* RbSensor<State>::set_observation(image): rows*cols float32 metres, row-major
+ * (row*cols+col, ref:source/dbot_ros/util/ros_interface.h:152-168), NaN = no data.
+ * Advances the observation time by delta_time. */
+int dbot_b200_set_observation(dbot_b200_sensor* s, const float* depth_m);
+
+/* RbSensor<State>::loglikes(deltas, indices, update).
+ *   poses        [n][n_objects][12] float32: R row-major (9) then t (3), absolute pose in the
+ *                camera frame (delta (x) default pose already composed by the adapter)
+ *   indices      [n] in: occlusion slot of each particle's parent; out: identity when update
+ *   out_loglikes [n] double
+ * update == 0 leaves all state untouched. */
+int dbot_b200_loglikes(dbot_b200_sensor* s, const float* poses, int32_t* indices, int32_t n,
+                       int32_t update, double* out_loglikes);
+
+/* dbot RigidBodyRenderer::Render for one pose set: out_depth[rows*cols], +INFINITY where no
+ * triangle is hit.  Used for visualisation and by the parity tests. */
+int dbot_b200_render(dbot_b200_sensor* s, const float* pose, float* out_depth);
+
+/* ---- device-resident variants: all pointers are device pointers on cfg.device_id; work is
+ * enqueued on the handle's stream and NOT synchronised (use dbot_b200_synchronize). ---- */
+int dbot_b200_set_observation_device(dbot_b200_sensor* s, const float* d_depth_m);
+int dbot_b200_loglikes_device(dbot_b200_sensor* s, const float* d_poses, int32_t* d_indices,
+                              int32_t n, int32_t update, double* d_out_loglikes);
+void* dbot_b200_stream(dbot_b200_sensor* s); /* cudaStream_t */
+int dbot_b200_synchronize(dbot_b200_sensor* s);
+
+/* ---- state read-back (tests, debugging) ---- */
+int dbot_b200_n_slots(dbot_b200_sensor* s);
+double dbot_b200_observation_time(dbot_b200_sensor* s);
+/* occlusion probability image of one slot as of the current observation time, rows*cols floats */
+int dbot_b200_get_occlusion(dbot_b200_sensor* s, int32_t slot, float* out_occ);
+
+/* ---- measurement hooks (bench.py) ---- */
+/* CUDA events on the handle's stream: begin records, end records + synchronises and returns ms */
+int dbot_b200_timer_begin(dbot_b200_sensor* s);
+int dbot_b200_timer_end(dbot_b200_sensor* s, float* out_ms);
+/* per-kernel accounting: when enabled every kernel launch is bracketed by events */
+#define DBOT_B200_KERNEL_OBSERVATION 0 /* observation table precompute           */
+#define DBOT_B200_KERNEL_LOGLIKES 1    /* raster + likelihood, update == 0       */
+#define DBOT_B200_KERNEL_UPDATE 2      /* raster + likelihood + occlusion stream */
+#define DBOT_B200_KERNEL_RENDER 3
+#define DBOT_B200_KERNEL_COUNT 4
+int dbot_b200_profile_enable(dbot_b200_sensor* s, int32_t on);
+/* sums since the last call; arrays of DBOT_B200_KERNEL_COUNT entries */
+int dbot_b200_profile_read(dbot_b200_sensor* s, float* out_ms, int64_t* out_launches);
+/* total kernels launched by this handle since create */
+int64_t dbot_b200_launch_count(dbot_b200_sensor* s);
+/* bytes of device memory held by the handle */
+int64_t dbot_b200_device_bytes(dbot_b200_sensor* s);
+
+int dbot_b200_abi_version(void);
+const char* dbot_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
