@@ -1,0 +1,959 @@
+/*
+ * dbot_b200.cu -- libdbot_b200.so: the B200 (sm_100a) depth observation model of the
+ * dbot / dbot_ros particle tracker behind the C-ABI of include/dbot_b200.h.
+ *
+ * Replaces dbot's KinectImageModelGPU (OpenGL rasteriser + CUDA evaluator), which dbot_ros
+ * selects with use_gpu:true (ref:config/particle_tracker.yaml:3,
+ * ref:source/dbot_ros/tracker/particle_tracker_node.cpp:164-203).  Nothing here is derived
+ * from that code: one persistent CTA per SM walks the particles; per particle it
+ *   1. stages the mesh chunk (vertices + uint16 triangle indices) in shared memory with
+ *      TMA bulk copies (cp.async.bulk + mbarrier) -- resident across particles when the
+ *      mesh is a single chunk,
+ *   2. transforms + projects + snaps the vertices (shared memory SoA),
+ *   3. rasterises all triangles into a shared-memory z tile covering the particle's
+ *      screen window with exact integer edge functions and atomicMin on the depth bits,
+ *   4. evaluates the per-pixel visible/occluded mixture against the per-frame observation
+ *      table and the parent's occlusion image, and on update streams the propagated /
+ *      posterior occlusion image of the child slot,
+ *   5. reduces to one double log-weight with a fixed shuffle tree (deterministic).
+ * There is no CPU fallback in this library.
+ */
+#include "../../include/dbot_b200.h"
+#include "particle_core.cuh"
+
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#define DBOT_NT 512              /* threads per CTA */
+#define DBOT_CHUNK_MAX_VERTS 3072
+#define DBOT_CHUNK_MAX_TRIS 6144
+#define DBOT_STREAM_UNROLL 4
+
+enum
+{
+    DBOT_MODE_EVAL = 0,
+    DBOT_MODE_UPDATE = 1,
+    DBOT_MODE_RENDER = 2
+};
+
+struct dbot_chunk
+{
+    int32_t obj, n_verts, n_tris, pad;
+    uint32_t vert_off, vert_bytes; /* byte offsets into the packed device mesh, 16 B aligned */
+    uint32_t tri_off, tri_bytes;
+};
+
+struct dbot_kparams
+{
+    int rows, cols, pitch; /* pitch: floats per state / table row, multiple of 4 */
+    int n_obj, n_chunks;
+    int n, n_slots;
+    dbot_camera K;
+    dbot_pixel_model M;
+    const dbot_chunk* chunks;
+    const unsigned char* mesh;
+    const float4* tab;      /* [rows*pitch] observation table */
+    const float* occ_in;    /* [n_slots][slot_stride] */
+    float* occ_out;         /* [n][slot_stride] (update) */
+    size_t slot_stride;     /* rows*pitch */
+    const float* poses;     /* [n][n_obj][12] */
+    int32_t* indices;       /* [n] */
+    double* out;            /* [n] */
+    float* depth_out;       /* render: [rows*cols] */
+    int* err_flag;
+    /* shared-memory carve-up (bytes from the dynamic smem base) */
+    uint32_t off_tri, off_vert, off_X, off_Y, off_x, off_y, off_z, off_zt;
+    uint32_t zcap;          /* z tile capacity in pixels */
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* PTX wrappers: mbarrier + TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP)                     */
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* K1: per-frame observation table.  Everything in the pixel densities that depends only on
+ * the observed depth y (dbot KinectPixelModel) is evaluated once per frame in
+ * double and stored as float4 { y, 1/(sqrt2 sigma), C_v/p_inf, (w/D)/p_inf }.                */
+__global__ void dbot_observation_kernel(const float* __restrict__ depth, float4* __restrict__ tab,
+                                        int rows, int cols, int pitch, double tail_weight,
+                                        double model_sigma, double sigma_factor, double lambda,
+                                        double wD)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * pitch) return;
+    const int r = idx / pitch, c = idx - r * pitch;
+    float4 t = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+    if (c < cols)
+    {
+        const float yf = depth[r * cols + c];
+        if (yf == yf)
+        {
+            const double y = (double)yf;
+            const double sigma = model_sigma + sigma_factor * y * y;
+            const double g = 1.0 / (1.4142135623730951 * sigma);
+            const double cv = (1.0 - tail_weight) / (2.5066282746310002 * sigma);
+            const double co =
+                0.5 * (1.0 - tail_weight) * lambda * exp(0.5 * lambda * (-2.0 * y + lambda * sigma * sigma));
+            const double pinf = wD + 2.0 * co;
+            t = make_float4(yf, (float)g, (float)(cv / pinf), (float)(wD / pinf));
+        }
+    }
+    tab[idx] = t;
+}
+
+__global__ void dbot_fill_kernel(float* __restrict__ dst, size_t n, float v)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = v;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* K2: fused transform + raster + likelihood (+ occlusion stream) kernel                       */
+template <int MODE>
+__global__ void __launch_bounds__(DBOT_NT, 1) dbot_particle_kernel(const __grid_constant__ dbot_kparams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_bb[4];
+    __shared__ double s_red[DBOT_NT / 32];
+
+    uint16_t* s_tri = (uint16_t*)(smem + p.off_tri);
+    float* s_vert = (float*)(smem + p.off_vert);
+    int* s_X = (int*)(smem + p.off_X);
+    int* s_Y = (int*)(smem + p.off_Y);
+    float* s_x = (float*)(smem + p.off_x);
+    float* s_y = (float*)(smem + p.off_y);
+    float* s_z = (float*)(smem + p.off_z);
+    uint32_t* s_zt = (uint32_t*)(smem + p.off_zt);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    uint32_t parity = 0;
+    int staged = -1;
+
+    /* TMA-stage one mesh chunk: one thread arms the mbarrier with the byte count and issues
+     * two bulk copies (vertices, indices); everybody waits on the barrier phase. */
+    auto stage_chunk = [&](int c) {
+        if (staged == c) return;
+        __syncthreads(); /* all readers of the previous chunk are done */
+        if (tid == 0)
+        {
+            const dbot_chunk ch = p.chunks[c];
+            mbar_expect_tx(&s_bar, ch.vert_bytes + ch.tri_bytes);
+            tma_load_1d(s_vert, p.mesh + ch.vert_off, ch.vert_bytes, &s_bar);
+            tma_load_1d(s_tri, p.mesh + ch.tri_off, ch.tri_bytes, &s_bar);
+        }
+        mbar_wait(&s_bar, parity);
+        parity ^= 1u;
+        staged = c;
+    };
+
+    for (int i = blockIdx.x; i < p.n; i += gridDim.x)
+    {
+        const float* pose = p.poses + (size_t)i * 12 * p.n_obj;
+        int slot = 0;
+        if (MODE != DBOT_MODE_RENDER)
+        {
+            slot = p.indices[i];
+            if (slot < 0 || slot >= p.n_slots)
+            {
+                if (tid == 0)
+                {
+                    p.out[i] = __longlong_as_double(0x7ff8000000000000LL);
+                    atomicExch(p.err_flag, 1);
+                }
+                continue;
+            }
+        }
+        const float* occ_in = p.occ_in + (size_t)slot * p.slot_stride;
+        float* occ_out = (MODE == DBOT_MODE_UPDATE) ? p.occ_out + (size_t)i * p.slot_stride : nullptr;
+
+        /* ---- pass 1: transform every chunk, collect the screen window of the particle ---- */
+        if (tid == 0)
+        {
+            s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN;
+        }
+        __syncthreads(); /* also fences the previous particle's use of shared memory */
+        dbot_bbox bb = {INT_MAX, INT_MIN, INT_MAX, INT_MIN};
+        for (int c = 0; c < p.n_chunks; ++c)
+        {
+            stage_chunk(c);
+            const dbot_chunk ch = p.chunks[c];
+            dbot_transform_vertices(s_vert, ch.n_verts, pose + 12 * ch.obj, p.K, s_X, s_Y, s_x, s_y,
+                                    s_z, tid, DBOT_NT, bb);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+        {
+            bb.min_x = min(bb.min_x, __shfl_xor_sync(0xffffffffu, bb.min_x, off));
+            bb.max_x = max(bb.max_x, __shfl_xor_sync(0xffffffffu, bb.max_x, off));
+            bb.min_y = min(bb.min_y, __shfl_xor_sync(0xffffffffu, bb.min_y, off));
+            bb.max_y = max(bb.max_y, __shfl_xor_sync(0xffffffffu, bb.max_y, off));
+        }
+        if (lane == 0)
+        {
+            atomicMin(&s_bb[0], bb.min_x); atomicMax(&s_bb[1], bb.max_x);
+            atomicMin(&s_bb[2], bb.min_y); atomicMax(&s_bb[3], bb.max_y);
+        }
+        __syncthreads();
+        int c0 = 0, c1 = -1, r0 = 0, r1 = -1;
+        if (s_bb[0] <= s_bb[1])
+        {
+            c0 = max(dbot_ceil_subpix(s_bb[0]), 0);
+            c1 = min(dbot_floor_subpix(s_bb[1]), p.cols - 1);
+            r0 = max(dbot_ceil_subpix(s_bb[2]), 0);
+            r1 = min(dbot_floor_subpix(s_bb[3]), p.rows - 1);
+        }
+        const bool have_window = (c0 <= c1) && (r0 <= r1);
+        const int ww = c1 - c0 + 1;
+        float acc = 0.0f;
+
+        if (have_window)
+        {
+            const int band_rows = max(1, (int)(p.zcap / (uint32_t)ww));
+            for (int rb0 = r0; rb0 <= r1; rb0 += band_rows)
+            {
+                const int rb1 = min(rb0 + band_rows - 1, r1);
+                const int npx = (rb1 - rb0 + 1) * ww;
+                __syncthreads(); /* previous band's readers of the z tile are done */
+                for (int q = tid; q < npx; q += DBOT_NT) s_zt[q] = DBOT_Z_EMPTY;
+                if (p.n_chunks == 1)
+                {
+                    __syncthreads();
+                    dbot_raster_triangles(s_tri, p.chunks[0].n_tris, s_X, s_Y, s_x, s_y, s_z, p.K,
+                                          s_zt, rb0, rb1, c0, c1, tid, DBOT_NT);
+                }
+                else
+                {
+                    for (int c = 0; c < p.n_chunks; ++c)
+                    {
+                        stage_chunk(c); /* leading barrier orders z-tile init / previous raster */
+                        const dbot_chunk ch = p.chunks[c];
+                        dbot_bbox dummy = {INT_MAX, INT_MIN, INT_MAX, INT_MIN};
+                        dbot_transform_vertices(s_vert, ch.n_verts, pose + 12 * ch.obj, p.K, s_X,
+                                                s_Y, s_x, s_y, s_z, tid, DBOT_NT, dummy);
+                        __syncthreads();
+                        dbot_raster_triangles(s_tri, ch.n_tris, s_X, s_Y, s_x, s_y, s_z, p.K, s_zt,
+                                              rb0, rb1, c0, c1, tid, DBOT_NT);
+                    }
+                }
+                __syncthreads();
+                /* ---- per-pixel mixture over the band (coalesced along image rows) ---- */
+                for (int q = tid; q < npx; q += DBOT_NT)
+                {
+                    const int rr = q / ww;
+                    const int cc = q - rr * ww;
+                    const int r = rb0 + rr, c = c0 + cc;
+                    const uint32_t zb = s_zt[q];
+                    if (MODE == DBOT_MODE_RENDER)
+                    {
+                        p.depth_out[(size_t)r * p.cols + c] = dbot_u2f(zb);
+                        continue;
+                    }
+                    const size_t gp = (size_t)r * p.pitch + c;
+                    float o_in = 0.0f;
+                    if (MODE == DBOT_MODE_UPDATE) o_in = __ldcs(occ_in + gp);
+                    bool valid = false;
+                    float4 tab;
+                    if (zb != DBOT_Z_EMPTY)
+                    {
+                        tab = __ldg(p.tab + gp);
+                        valid = (tab.x == tab.x);
+                    }
+                    float o_new;
+                    if (valid)
+                    {
+                        if (MODE != DBOT_MODE_UPDATE) o_in = __ldcs(occ_in + gp);
+                        acc += dbot_pixel_term(dbot_u2f(zb), tab, o_in, p.M, o_new);
+                    }
+                    else
+                        o_new = dbot_fmaf(p.M.prop_a, o_in, p.M.prop_b);
+                    if (MODE == DBOT_MODE_UPDATE) __stcs(occ_out + gp, o_new);
+                }
+            }
+        }
+
+        /* ---- update: stream the rest of the child's occlusion image (propagated parent) ---- */
+        if (MODE == DBOT_MODE_UPDATE)
+        {
+            const int nq = (int)(p.slot_stride >> 2);
+            const float4* in4 = reinterpret_cast<const float4*>(occ_in);
+            float4* out4 = reinterpret_cast<float4*>(occ_out);
+            const float A = p.M.prop_a, B = p.M.prop_b;
+            for (int base = 0; base < nq; base += DBOT_NT * DBOT_STREAM_UNROLL)
+            {
+                float4 v[DBOT_STREAM_UNROLL];
+#pragma unroll
+                for (int k = 0; k < DBOT_STREAM_UNROLL; ++k)
+                {
+                    const int q = base + k * DBOT_NT + tid;
+                    if (q < nq) v[k] = __ldcs(in4 + q);
+                }
+#pragma unroll
+                for (int k = 0; k < DBOT_STREAM_UNROLL; ++k)
+                {
+                    const int q = base + k * DBOT_NT + tid;
+                    if (q >= nq) continue;
+                    const int e = q << 2;
+                    const int r = e / p.pitch;
+                    const int c = e - r * p.pitch;
+                    float4 w;
+                    w.x = dbot_fmaf(A, v[k].x, B);
+                    w.y = dbot_fmaf(A, v[k].y, B);
+                    w.z = dbot_fmaf(A, v[k].z, B);
+                    w.w = dbot_fmaf(A, v[k].w, B);
+                    if (have_window && r >= r0 && r <= r1 && c + 3 >= c0 && c <= c1)
+                    {
+                        /* group touches the window: the window pixels were written above */
+                        float* o = occ_out + e;
+                        if (c < c0 || c > c1) __stcs(o, w.x);
+                        if (c + 1 < c0 || c + 1 > c1) __stcs(o + 1, w.y);
+                        if (c + 2 < c0 || c + 2 > c1) __stcs(o + 2, w.z);
+                        if (c + 3 < c0 || c + 3 > c1) __stcs(o + 3, w.w);
+                    }
+                    else
+                        __stcs(out4 + q, w);
+                }
+            }
+        }
+
+        /* ---- one log-weight per particle: fixed shuffle tree, double across warps ---- */
+        if (MODE != DBOT_MODE_RENDER)
+        {
+            double v = (double)acc;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (lane == 0) s_red[warp] = v;
+            __syncthreads();
+            if (tid == 0)
+            {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < DBOT_NT / 32; ++w) s += s_red[w];
+                p.out[i] = s;
+                if (MODE == DBOT_MODE_UPDATE) p.indices[i] = i;
+            }
+        }
+    }
+}
+
+/* ========================================================================================== */
+/* host side                                                                                  */
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do                                                                                         \
+    {                                                                                          \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail((int)e__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),     \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+struct dbot_b200_sensor
+{
+    dbot_b200_config cfg;
+    int device;
+    cudaStream_t stream;
+    dbot_kparams kp; /* template: per-call fields are filled at launch */
+    int grid_max, smem_bytes, num_sms;
+    /* model constants */
+    double lambda, wD, c, log_c;
+    /* device memory */
+    unsigned char* d_mesh;
+    dbot_chunk* d_chunks;
+    float* d_obs;
+    float4* d_tab;
+    float* d_occ[2];
+    float* d_poses;
+    int32_t* d_indices;
+    double* d_out;
+    float* d_depth;
+    int* d_err;
+    /* pinned staging */
+    float* h_poses;
+    int32_t* h_indices;
+    double* h_out;
+    float* h_obs;
+    float* h_depth;
+    int* h_err;
+    /* state */
+    int cur, n_slots;
+    double t_obs, t_update;
+    /* measurement */
+    cudaEvent_t ev_begin, ev_end, ev_k0, ev_k1;
+    int profile;
+    float prof_ms[DBOT_B200_KERNEL_COUNT];
+    int64_t prof_launches[DBOT_B200_KERNEL_COUNT];
+    int64_t launches;
+    int64_t device_bytes;
+};
+
+static uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+/* split every object mesh into chunks of at most DBOT_CHUNK_MAX_VERTS vertices and
+ * DBOT_CHUNK_MAX_TRIS triangles with chunk-local uint16 indices (shared vertices are
+ * duplicated; a duplicated vertex transforms to bit-identical coordinates). */
+static int build_chunks(const dbot_b200_config* cfg, std::vector<dbot_chunk>& chunks,
+                        std::vector<unsigned char>& blob)
+{
+    for (int o = 0; o < cfg->n_objects; ++o)
+    {
+        const int nv = cfg->n_vertices[o], nt = cfg->n_triangles[o];
+        if (nv < 0 || nt < 0) return fail(-2, "object %d: negative vertex/triangle count", o);
+        const float* V = cfg->vertices[o];
+        const int32_t* T = cfg->triangles[o];
+        if ((nv > 0 && !V) || (nt > 0 && !T)) return fail(-1, "object %d: null mesh pointer", o);
+        for (int i = 0; i < 3 * nt; ++i)
+            if (T[i] < 0 || T[i] >= nv) return fail(-6, "object %d: triangle index out of range", o);
+        int t = 0;
+        while (t < nt)
+        {
+            std::unordered_map<int32_t, uint16_t> local;
+            std::vector<float> cv;
+            std::vector<uint16_t> ct;
+            while (t < nt && (int)ct.size() / 3 < DBOT_CHUNK_MAX_TRIS)
+            {
+                int fresh = 0;
+                for (int k = 0; k < 3; ++k)
+                    if (!local.count(T[3 * t + k])) ++fresh;
+                /* worst case all three are new (repeated indices inside one triangle count once) */
+                if ((int)local.size() + fresh > DBOT_CHUNK_MAX_VERTS) break;
+                for (int k = 0; k < 3; ++k)
+                {
+                    const int32_t g = T[3 * t + k];
+                    auto it = local.find(g);
+                    if (it == local.end())
+                    {
+                        it = local.emplace(g, (uint16_t)local.size()).first;
+                        cv.push_back(V[3 * g]);
+                        cv.push_back(V[3 * g + 1]);
+                        cv.push_back(V[3 * g + 2]);
+                    }
+                    ct.push_back(it->second);
+                }
+                ++t;
+            }
+            dbot_chunk ch;
+            memset(&ch, 0, sizeof(ch));
+            ch.obj = o;
+            ch.n_verts = (int)cv.size() / 3;
+            ch.n_tris = (int)ct.size() / 3;
+            ch.vert_bytes = round_up((uint32_t)(cv.size() * sizeof(float)), 16);
+            ch.tri_bytes = round_up((uint32_t)(ct.size() * sizeof(uint16_t)), 16);
+            ch.vert_off = (uint32_t)blob.size();
+            blob.resize(blob.size() + ch.vert_bytes, 0);
+            memcpy(blob.data() + ch.vert_off, cv.data(), cv.size() * sizeof(float));
+            ch.tri_off = (uint32_t)blob.size();
+            blob.resize(blob.size() + ch.tri_bytes, 0);
+            memcpy(blob.data() + ch.tri_off, ct.data(), ct.size() * sizeof(uint16_t));
+            chunks.push_back(ch);
+        }
+    }
+    if (chunks.empty())
+    {
+        /* no triangles at all: keep one empty chunk so the kernel has something to walk */
+        dbot_chunk ch;
+        memset(&ch, 0, sizeof(ch));
+        ch.vert_bytes = ch.tri_bytes = 16;
+        ch.vert_off = 0;
+        ch.tri_off = 16;
+        blob.resize(32, 0);
+        chunks.push_back(ch);
+    }
+    return 0;
+}
+
+extern "C" int dbot_b200_abi_version(void) { return DBOT_B200_ABI_VERSION; }
+extern "C" const char* dbot_b200_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int dbot_b200_destroy(dbot_b200_sensor* s)
+{
+    if (!s) return fail(-1, "destroy: null handle");
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_mesh); cudaFree(s->d_chunks); cudaFree(s->d_obs); cudaFree(s->d_tab);
+    cudaFree(s->d_occ[0]); cudaFree(s->d_occ[1]); cudaFree(s->d_poses); cudaFree(s->d_indices);
+    cudaFree(s->d_out); cudaFree(s->d_depth); cudaFree(s->d_err);
+    cudaFreeHost(s->h_poses); cudaFreeHost(s->h_indices); cudaFreeHost(s->h_out);
+    cudaFreeHost(s->h_obs); cudaFreeHost(s->h_depth); cudaFreeHost(s->h_err);
+    if (s->ev_begin) cudaEventDestroy(s->ev_begin);
+    if (s->ev_end) cudaEventDestroy(s->ev_end);
+    if (s->ev_k0) cudaEventDestroy(s->ev_k0);
+    if (s->ev_k1) cudaEventDestroy(s->ev_k1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return 0;
+}
+
+static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
+{
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(e != cudaSuccess ? (int)e : (int)cudaErrorNoDevice,
+                    "no CUDA device: libdbot_b200 has no CPU fallback (%s)", cudaGetErrorString(e));
+    if (cfg->device_id < 0 || cfg->device_id >= n_dev)
+        return fail(-2, "device_id %d out of range (have %d)", cfg->device_id, n_dev);
+    s->device = cfg->device_id;
+    CUDA_TRY(cudaSetDevice(s->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
+    if (prop.major < 10)
+        return fail(-8, "device %d is sm_%d%d; this library is built for sm_100a only", s->device,
+                    prop.major, prop.minor);
+    s->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&s->ev_begin));
+    CUDA_TRY(cudaEventCreate(&s->ev_end));
+    CUDA_TRY(cudaEventCreate(&s->ev_k0));
+    CUDA_TRY(cudaEventCreate(&s->ev_k1));
+
+    /* mesh */
+    std::vector<dbot_chunk> chunks;
+    std::vector<unsigned char> blob;
+    int rc = build_chunks(cfg, chunks, blob);
+    if (rc) return rc;
+    CUDA_TRY(cudaMalloc(&s->d_mesh, blob.size()));
+    CUDA_TRY(cudaMemcpy(s->d_mesh, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&s->d_chunks, chunks.size() * sizeof(dbot_chunk)));
+    CUDA_TRY(cudaMemcpy(s->d_chunks, chunks.data(), chunks.size() * sizeof(dbot_chunk),
+                        cudaMemcpyHostToDevice));
+    s->device_bytes += (int64_t)blob.size() + (int64_t)(chunks.size() * sizeof(dbot_chunk));
+
+    dbot_kparams& kp = s->kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.rows = cfg->rows;
+    kp.cols = cfg->cols;
+    kp.pitch = (int)round_up((uint32_t)cfg->cols, 4);
+    kp.n_obj = cfg->n_objects;
+    kp.n_chunks = (int)chunks.size();
+    kp.slot_stride = (size_t)kp.rows * kp.pitch;
+    kp.chunks = s->d_chunks;
+    kp.mesh = s->d_mesh;
+    const double fx = cfg->K[0], sk = cfg->K[1], cx = cfg->K[2], fy = cfg->K[4], cy = cfg->K[5];
+    kp.K.fx = (float)fx; kp.K.sk = (float)sk; kp.K.cx = (float)cx; kp.K.fy = (float)fy; kp.K.cy = (float)cy;
+    kp.K.k00 = (float)(1.0 / fx);
+    kp.K.k01 = (float)(-sk / (fx * fy));
+    kp.K.k02 = (float)((sk * cy - cx * fy) / (fx * fy));
+    kp.K.k11 = (float)(1.0 / fy);
+    kp.K.k12 = (float)(-cy / fy);
+    s->lambda = -log(0.5) / cfg->half_life_depth; /* dbot KinectPixelModel: rate from half life */
+    s->wD = cfg->tail_weight / cfg->max_depth;
+    s->c = cfg->p_occluded_occluded - cfg->p_occluded_visible;
+    s->log_c = log(s->c);
+    kp.M.lam_rsqrt2 = (float)(s->lambda / 1.4142135623730951);
+    kp.M.nlam_log2e = (float)(-s->lambda * 1.4426950408889634);
+    kp.M.model_sigma = (float)cfg->model_sigma;
+    kp.M.sigma_factor = (float)cfg->sigma_factor;
+
+    /* shared-memory carve-up: indices | vertices | X Y x y z | z tile */
+    int max_nv = 1, max_nt = 1;
+    for (const dbot_chunk& ch : chunks)
+    {
+        max_nv = std::max(max_nv, ch.n_verts);
+        max_nt = std::max(max_nt, ch.n_tris);
+    }
+    uint32_t off = 0;
+    kp.off_tri = off;  off += round_up((uint32_t)max_nt * 6u, 128);
+    kp.off_vert = off; off += round_up((uint32_t)max_nv * 12u, 128);
+    const uint32_t col = round_up((uint32_t)max_nv * 4u, 128);
+    kp.off_X = off; off += col;
+    kp.off_Y = off; off += col;
+    kp.off_x = off; off += col;
+    kp.off_y = off; off += col;
+    kp.off_z = off; off += col;
+    kp.off_zt = off;
+    const int smem_max = (int)prop.sharedMemPerBlockOptin - 2048; /* static __shared__ + slack */
+    if ((int)off + 4 * kp.cols > smem_max)
+        return fail(-9, "image too wide for the shared-memory z tile (cols=%d)", kp.cols);
+    s->smem_bytes = smem_max;
+    kp.zcap = (uint32_t)(smem_max - (int)off) / 4u;
+    CUDA_TRY(cudaFuncSetAttribute(dbot_particle_kernel<DBOT_MODE_EVAL>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(dbot_particle_kernel<DBOT_MODE_UPDATE>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(dbot_particle_kernel<DBOT_MODE_RENDER>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
+    s->grid_max = s->num_sms; /* one persistent CTA per SM (launch bounds: 1 CTA/SM) */
+
+    /* buffers */
+    const size_t P = (size_t)kp.rows * kp.cols;
+    const size_t np = (size_t)cfg->max_particles;
+    const size_t state_bytes = np * kp.slot_stride * sizeof(float);
+    CUDA_TRY(cudaMalloc(&s->d_obs, P * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&s->d_tab, kp.slot_stride * sizeof(float4)));
+    CUDA_TRY(cudaMalloc(&s->d_occ[0], state_bytes));
+    CUDA_TRY(cudaMalloc(&s->d_occ[1], state_bytes));
+    CUDA_TRY(cudaMalloc(&s->d_poses, np * 12 * kp.n_obj * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&s->d_indices, np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_out, np * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s->d_depth, P * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&s->d_err, sizeof(int)));
+    CUDA_TRY(cudaMemset(s->d_err, 0, sizeof(int)));
+    s->device_bytes += (int64_t)(2 * P * sizeof(float) + kp.slot_stride * sizeof(float4) +
+                                 2 * state_bytes + np * (12 * kp.n_obj * 4 + 4 + 8) + 4);
+    CUDA_TRY(cudaHostAlloc(&s->h_poses, np * 12 * kp.n_obj * sizeof(float), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&s->h_indices, np * sizeof(int32_t), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&s->h_out, np * sizeof(double), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&s->h_obs, P * sizeof(float), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&s->h_depth, P * sizeof(float), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&s->h_err, sizeof(int), cudaHostAllocDefault));
+    /* until the first set_observation every pixel is "no data" */
+    CUDA_TRY(cudaMemsetAsync(s->d_obs, 0xff, P * sizeof(float), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->d_tab, 0xff, kp.slot_stride * sizeof(float4), s->stream));
+    return dbot_b200_reset(s);
+}
+
+extern "C" int dbot_b200_create(const dbot_b200_config* cfg, dbot_b200_sensor** out)
+{
+    if (!cfg || !out) return fail(-1, "create: null argument");
+    *out = nullptr;
+    if (cfg->rows <= 0 || cfg->cols <= 0) return fail(-2, "create: bad resolution %dx%d", cfg->cols, cfg->rows);
+    if (cfg->n_objects <= 0 || cfg->n_objects > DBOT_B200_MAX_OBJECTS)
+        return fail(-2, "create: n_objects=%d not in [1,%d]", cfg->n_objects, DBOT_B200_MAX_OBJECTS);
+    if (cfg->max_particles <= 0) return fail(-2, "create: max_particles must be positive");
+    if (!cfg->vertices || !cfg->n_vertices || !cfg->triangles || !cfg->n_triangles)
+        return fail(-1, "create: null mesh arrays");
+    if (cfg->K[3] != 0.0 || cfg->K[6] != 0.0 || cfg->K[7] != 0.0 || cfg->K[8] != 1.0 ||
+        cfg->K[0] == 0.0 || cfg->K[4] == 0.0)
+        return fail(-3, "create: camera matrix must be [[fx s cx][0 fy cy][0 0 1]]");
+    const double c = cfg->p_occluded_occluded - cfg->p_occluded_visible;
+    if (!(c > 0.0) || c == 1.0) return fail(-4, "create: need 0 < p_occluded_occluded - p_occluded_visible < 1");
+    if (!(cfg->half_life_depth > 0.0) || !(cfg->max_depth > 0.0) || !(cfg->model_sigma > 0.0))
+        return fail(-4, "create: half_life_depth, max_depth and model_sigma must be positive");
+    if (cfg->occlusion_mode != 0) return fail(-2, "create: occlusion_mode %d is reserved", cfg->occlusion_mode);
+    dbot_b200_sensor* s = new dbot_b200_sensor();
+    memset(s, 0, sizeof(*s));
+    s->cfg = *cfg;
+    s->cfg.vertices = nullptr; s->cfg.triangles = nullptr;
+    s->cfg.n_vertices = nullptr; s->cfg.n_triangles = nullptr;
+    int rc = create_impl(cfg, s);
+    if (rc)
+    {
+        std::string keep = g_last_error;
+        dbot_b200_destroy(s);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = s;
+    return 0;
+}
+
+static void prof_begin(dbot_b200_sensor* s)
+{
+    if (s->profile) cudaEventRecord(s->ev_k0, s->stream);
+}
+static void prof_end(dbot_b200_sensor* s, int which)
+{
+    s->launches++;
+    if (!s->profile) return;
+    cudaEventRecord(s->ev_k1, s->stream);
+    cudaEventSynchronize(s->ev_k1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s->ev_k0, s->ev_k1);
+    s->prof_ms[which] += ms;
+    s->prof_launches[which]++;
+}
+
+/* RbSensor::reset */
+extern "C" int dbot_b200_reset(dbot_b200_sensor* s)
+{
+    if (!s) return fail(-1, "reset: null handle");
+    CUDA_TRY(cudaSetDevice(s->device));
+    s->cur = 0;
+    s->n_slots = 1;
+    s->t_obs = 0.0;
+    s->t_update = 0.0;
+    dbot_fill_kernel<<<64, 256, 0, s->stream>>>(s->d_occ[0], s->kp.slot_stride,
+                                                (float)s->cfg.initial_occlusion_prob);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+static int launch_observation(dbot_b200_sensor* s, const float* d_depth)
+{
+    const int total = (int)s->kp.slot_stride;
+    prof_begin(s);
+    dbot_observation_kernel<<<(total + 255) / 256, 256, 0, s->stream>>>(
+        d_depth, s->d_tab, s->kp.rows, s->kp.cols, s->kp.pitch, s->cfg.tail_weight,
+        s->cfg.model_sigma, s->cfg.sigma_factor, s->lambda, s->wD);
+    CUDA_TRY(cudaGetLastError());
+    prof_end(s, DBOT_B200_KERNEL_OBSERVATION);
+    s->t_obs += s->cfg.delta_time;
+    return 0;
+}
+
+/* RbSensor::set_observation */
+extern "C" int dbot_b200_set_observation(dbot_b200_sensor* s, const float* depth_m)
+{
+    if (!s || !depth_m) return fail(-1, "set_observation: null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t bytes = (size_t)s->kp.rows * s->kp.cols * sizeof(float);
+    memcpy(s->h_obs, depth_m, bytes);
+    CUDA_TRY(cudaMemcpyAsync(s->d_obs, s->h_obs, bytes, cudaMemcpyHostToDevice, s->stream));
+    int rc = launch_observation(s, s->d_obs);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int dbot_b200_set_observation_device(dbot_b200_sensor* s, const float* d_depth_m)
+{
+    if (!s || !d_depth_m) return fail(-1, "set_observation_device: null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    return launch_observation(s, d_depth_m);
+}
+
+/* occlusion propagation over dt as an affine map (dbot OcclusionModel) */
+static void propagation_affine(const dbot_b200_sensor* s, double dt, float* a, float* b)
+{
+    const double ct = exp(dt * s->log_c);
+    const double k = (1.0 - s->cfg.p_occluded_occluded) * (ct - 1.0) / (s->c - 1.0);
+    *a = (float)ct;
+    *b = (float)(1.0 - ct - k);
+}
+
+static int launch_particles(dbot_b200_sensor* s, const float* d_poses, int32_t* d_indices, int n,
+                            int update, double* d_out)
+{
+    dbot_kparams kp = s->kp;
+    kp.n = n;
+    kp.n_slots = s->n_slots;
+    kp.tab = s->d_tab;
+    kp.occ_in = s->d_occ[s->cur];
+    kp.occ_out = s->d_occ[s->cur ^ 1];
+    kp.poses = d_poses;
+    kp.indices = d_indices;
+    kp.out = d_out;
+    kp.err_flag = s->d_err;
+    propagation_affine(s, s->t_obs - s->t_update, &kp.M.prop_a, &kp.M.prop_b);
+    const int grid = std::min(n, s->grid_max);
+    prof_begin(s);
+    if (update)
+        dbot_particle_kernel<DBOT_MODE_UPDATE><<<grid, DBOT_NT, s->smem_bytes, s->stream>>>(kp);
+    else
+        dbot_particle_kernel<DBOT_MODE_EVAL><<<grid, DBOT_NT, s->smem_bytes, s->stream>>>(kp);
+    CUDA_TRY(cudaGetLastError());
+    prof_end(s, update ? DBOT_B200_KERNEL_UPDATE : DBOT_B200_KERNEL_LOGLIKES);
+    if (update)
+    {
+        s->cur ^= 1;
+        s->n_slots = n;
+        s->t_update = s->t_obs;
+    }
+    return 0;
+}
+
+/* RbSensor::loglikes */
+extern "C" int dbot_b200_loglikes(dbot_b200_sensor* s, const float* poses, int32_t* indices,
+                                  int32_t n, int32_t update, double* out_loglikes)
+{
+    if (!s || !poses || !indices || !out_loglikes) return fail(-1, "loglikes: null argument");
+    if (n < 0 || n > s->cfg.max_particles)
+        return fail(-2, "loglikes: n=%d exceeds max_particles=%d", n, s->cfg.max_particles);
+    for (int i = 0; i < n; ++i)
+        if (indices[i] < 0 || indices[i] >= s->n_slots)
+            return fail(-7, "loglikes: indices[%d]=%d is not an occlusion slot (have %d)", i,
+                        indices[i], s->n_slots);
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t pose_bytes = (size_t)n * 12 * s->kp.n_obj * sizeof(float);
+    memcpy(s->h_poses, poses, pose_bytes);
+    memcpy(s->h_indices, indices, (size_t)n * sizeof(int32_t));
+    CUDA_TRY(cudaMemcpyAsync(s->d_poses, s->h_poses, pose_bytes, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->d_indices, s->h_indices, (size_t)n * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, s->stream));
+    int rc = launch_particles(s, s->d_poses, s->d_indices, n, update, s->d_out);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->h_out, s->d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost,
+                             s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    memcpy(out_loglikes, s->h_out, (size_t)n * sizeof(double));
+    if (update)
+        for (int i = 0; i < n; ++i) indices[i] = i;
+    return 0;
+}
+
+extern "C" int dbot_b200_loglikes_device(dbot_b200_sensor* s, const float* d_poses,
+                                         int32_t* d_indices, int32_t n, int32_t update,
+                                         double* d_out_loglikes)
+{
+    if (!s || !d_poses || !d_indices || !d_out_loglikes) return fail(-1, "loglikes_device: null argument");
+    if (n < 0 || n > s->cfg.max_particles)
+        return fail(-2, "loglikes_device: n=%d exceeds max_particles=%d", n, s->cfg.max_particles);
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(s->device));
+    return launch_particles(s, d_poses, d_indices, n, update, d_out_loglikes);
+}
+
+extern "C" void* dbot_b200_stream(dbot_b200_sensor* s) { return s ? (void*)s->stream : nullptr; }
+
+extern "C" int dbot_b200_synchronize(dbot_b200_sensor* s)
+{
+    if (!s) return fail(-1, "synchronize: null handle");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaMemcpyAsync(s->h_err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (*s->h_err)
+    {
+        cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream);
+        return fail(-7, "loglikes_device: an index was not a valid occlusion slot");
+    }
+    return 0;
+}
+
+/* RigidBodyRenderer::Render for one pose set */
+extern "C" int dbot_b200_render(dbot_b200_sensor* s, const float* pose, float* out_depth)
+{
+    if (!s || !pose || !out_depth) return fail(-1, "render: null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t P = (size_t)s->kp.rows * s->kp.cols;
+    const size_t pose_bytes = (size_t)12 * s->kp.n_obj * sizeof(float);
+    float* d_pose = nullptr;
+    CUDA_TRY(cudaMalloc(&d_pose, pose_bytes));
+    cudaError_t e = cudaMemcpyAsync(d_pose, pose, pose_bytes, cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess)
+    {
+        dbot_fill_kernel<<<64, 256, 0, s->stream>>>(s->d_depth, P, INFINITY);
+        s->launches++;
+        dbot_kparams kp = s->kp;
+        kp.n = 1;
+        kp.n_slots = 1;
+        kp.poses = d_pose;
+        kp.depth_out = s->d_depth;
+        kp.err_flag = s->d_err;
+        prof_begin(s);
+        dbot_particle_kernel<DBOT_MODE_RENDER><<<1, DBOT_NT, s->smem_bytes, s->stream>>>(kp);
+        e = cudaGetLastError();
+        prof_end(s, DBOT_B200_KERNEL_RENDER);
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(s->h_depth, s->d_depth, P * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_pose);
+    if (e != cudaSuccess) return fail((int)e, "render failed: %s", cudaGetErrorString(e));
+    memcpy(out_depth, s->h_depth, P * sizeof(float));
+    return 0;
+}
+
+/* ---- state read-back ---- */
+extern "C" int dbot_b200_n_slots(dbot_b200_sensor* s) { return s ? s->n_slots : -1; }
+extern "C" double dbot_b200_observation_time(dbot_b200_sensor* s) { return s ? s->t_obs : NAN; }
+
+extern "C" int dbot_b200_get_occlusion(dbot_b200_sensor* s, int32_t slot, float* out_occ)
+{
+    if (!s || !out_occ) return fail(-1, "get_occlusion: null argument");
+    if (slot < 0 || slot >= s->n_slots) return fail(-7, "get_occlusion: slot %d of %d", slot, s->n_slots);
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    const int rows = s->kp.rows, cols = s->kp.cols, pitch = s->kp.pitch;
+    std::vector<float> tmp((size_t)rows * cols);
+    CUDA_TRY(cudaMemcpy2D(tmp.data(), (size_t)cols * sizeof(float),
+                          s->d_occ[s->cur] + (size_t)slot * s->kp.slot_stride,
+                          (size_t)pitch * sizeof(float), (size_t)cols * sizeof(float), rows,
+                          cudaMemcpyDeviceToHost));
+    float a, b;
+    propagation_affine(s, s->t_obs - s->t_update, &a, &b);
+    for (size_t i = 0; i < tmp.size(); ++i) out_occ[i] = fmaf(a, tmp[i], b);
+    return 0;
+}
+
+/* ---- measurement hooks ---- */
+extern "C" int dbot_b200_timer_begin(dbot_b200_sensor* s)
+{
+    if (!s) return fail(-1, "timer_begin: null handle");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaEventRecord(s->ev_begin, s->stream));
+    return 0;
+}
+extern "C" int dbot_b200_timer_end(dbot_b200_sensor* s, float* out_ms)
+{
+    if (!s || !out_ms) return fail(-1, "timer_end: null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaEventRecord(s->ev_end, s->stream));
+    CUDA_TRY(cudaEventSynchronize(s->ev_end));
+    CUDA_TRY(cudaEventElapsedTime(out_ms, s->ev_begin, s->ev_end));
+    return 0;
+}
+extern "C" int dbot_b200_profile_enable(dbot_b200_sensor* s, int32_t on)
+{
+    if (!s) return fail(-1, "profile_enable: null handle");
+    s->profile = on ? 1 : 0;
+    memset(s->prof_ms, 0, sizeof(s->prof_ms));
+    memset(s->prof_launches, 0, sizeof(s->prof_launches));
+    return 0;
+}
+extern "C" int dbot_b200_profile_read(dbot_b200_sensor* s, float* out_ms, int64_t* out_launches)
+{
+    if (!s || !out_ms || !out_launches) return fail(-1, "profile_read: null argument");
+    memcpy(out_ms, s->prof_ms, sizeof(s->prof_ms));
+    memcpy(out_launches, s->prof_launches, sizeof(s->prof_launches));
+    memset(s->prof_ms, 0, sizeof(s->prof_ms));
+    memset(s->prof_launches, 0, sizeof(s->prof_launches));
+    return 0;
+}
+extern "C" int64_t dbot_b200_launch_count(dbot_b200_sensor* s) { return s ? s->launches : -1; }
+extern "C" int64_t dbot_b200_device_bytes(dbot_b200_sensor* s) { return s ? s->device_bytes : -1; }
