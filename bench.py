@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- particle-likelihoods/s of the depth observation model (BASELINE.json metric).
+
+A step is one depth frame through the sensor exactly as the particle filter drives it for a
+single-object tracker: set_observation(frame) then loglikes(poses, indices, update=true) for all
+particles (ref:source/dbot_ros/object_tracker_ros.hpp:49 -> dbot filter).
+
+  value   device-resident: frames, poses and parent indices already in HBM, the two kernels
+          launched through the *_device C-ABI entry points, timed with CUDA events on the
+          library's stream.
+  e2e     the same step through the reference-facing host call (host numpy buffers in, host
+          log-weights out; H2D/D2H inside the timed region).
+  roofline  the fused particle kernel (update): algorithmic bytes = 8*P per particle (read the
+          parent's fp32 occlusion image, write the child's), launch duration from CUDA events.
+  cpu_baseline / --impl reference   the CPU oracle (oracle/, OpenMP over particles, all host
+          cores) on a bounded particle sample of the same frames.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from dbot_ros_b200 import CameraData, ObjectModel, Parameters, RbSensorBuilder, synth  # noqa: E402
+
+METRIC = "particle_likelihoods_per_sec"
+UNIT = "particle-likelihoods/s"
+CONFIG_ID = 2            # BASELINE.json configs[1]: 1000 particles, 640x480, single 5k-tri mesh
+N_FRAMES = 4             # distinct synthetic frames / pose sets cycled through the steps
+
+
+def workload(config_id=CONFIG_ID):
+    mesh, n, ds = synth.CONFIGS[config_id]
+    rows, cols = synth.resolution(ds)
+    V, T = synth.mesh_set(mesh)
+    return dict(mesh=mesh, n=n, ds=ds, rows=rows, cols=cols, V=V, T=T, K=synth.camera_matrix(ds),
+                tris=int(sum(len(t) for t in T)))
+
+
+def describe(w, n_gpus):
+    return {"workload": "config%d: %d particles/GPU, %dx%d synthetic depth, %s (%d triangles), "
+                        "set_observation + loglikes(update=true) per step"
+                        % (CONFIG_ID, w["n"], w["cols"], w["rows"], w["mesh"], w["tris"]),
+            "particles_per_gpu": w["n"], "particles_total": w["n"] * n_gpus,
+            "resolution": [w["cols"], w["rows"]], "triangles": w["tris"],
+            "occlusion_mode": "dense-eager", "parallelism": "particles sharded x%d" % n_gpus,
+            "l2_policy": "inputs larger than L2 (%.2f GB occlusion state read + written per step)"
+                         % (2 * w["n"] * w["rows"] * w["cols"] * 4 / 1e9)}
+
+
+def resampled_parents(n, rng):
+    """systematic resampling of random weights: the parent pattern the filter produces"""
+    wgt = rng.gamma(0.5, size=n)
+    cdf = np.cumsum(wgt / wgt.sum())
+    u = (rng.random() + np.arange(n)) / n
+    return np.minimum(np.searchsorted(cdf, u), n - 1).astype(np.int32)
+
+
+def make_inputs(w, render, rank):
+    rng = synth.rng_for(CONFIG_ID, stream=rank)
+    gt = synth.ground_truth_poses(len(w["V"]), rng)
+    frames = [synth.make_frame(render, gt, w["rows"], w["cols"], rng) for _ in range(N_FRAMES)]
+    poses = [synth.particle_poses(gt, w["n"], rng) for _ in range(N_FRAMES)]
+    parents = [resampled_parents(w["n"], rng) for _ in range(N_FRAMES)]
+    return gt, frames, poses, parents
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], threading.Event()
+        self.thread = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(s[2 + k] == "Active" for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_oracle_rate(w, frames, poses, sample, reps, threads=None):
+    """oracle on the host cores: set_observation + loglikes(update) on `sample` particles"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+
+    orc = oracle_lib.Oracle(w["rows"], w["cols"], w["K"], w["V"], w["T"], synth.default_parameters())
+    cores = oracle_lib.oracle_lib().oracle_get_max_threads() if threads is None else threads
+    oracle_lib.oracle_lib().oracle_set_num_threads(cores)
+    idx = np.zeros(sample, dtype=np.int32)
+    orc.set_observation(frames[0])
+    orc.loglikes_poses(poses[0][:sample], idx, True)  # warm-up, leaves `sample` slots
+    times = []
+    for r in range(reps):
+        f = r % N_FRAMES
+        t0 = time.perf_counter()
+        orc.set_observation(frames[f])
+        orc.loglikes_poses(poses[f][:sample], idx, True)
+        times.append(time.perf_counter() - t0)
+    orc.close()
+    return sample / float(np.mean(times)), cores, float(np.mean(times))
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU evaluator for this path.  Its own implementation is in
+    the un-vendored dbot library and cannot be built here, so this arm times the
+    oracle port (OpenMP over particles, all host cores) on a bounded particle sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workload()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+
+    orc = oracle_lib.Oracle(w["rows"], w["cols"], w["K"], w["V"], w["T"], synth.default_parameters())
+    _, frames, poses, _ = make_inputs(w, orc.render, 0)
+    orc.close()
+    sample = 64
+    cores = os.cpu_count() or 1
+    cpu_oracle_rate(w, frames, poses, sample, max(args.warmup, 1))
+    rate, cores, sec = cpu_oracle_rate(w, frames, poses, sample, args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": describe(w, args.gpus),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d of the %d particles per step, same frames" % (sample, w["n"])},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (dbot_ros_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w = workload()
+    n, rows, cols = w["n"], w["rows"], w["cols"]
+    P = rows * cols
+    sensor = RbSensorBuilder(ObjectModel(w["V"], w["T"]), CameraData(w["K"], rows, cols),
+                             Parameters(sample_count=n), device_id=local_rank).build()
+    gt, frames, poses, parents = make_inputs(w, sensor.render, rank)
+    dev = torch.device("cuda", local_rank)
+    ext = torch.cuda.ExternalStream(sensor.stream, device=dev)
+    d_frames = [torch.from_numpy(f).to(dev) for f in frames]
+    d_poses = [torch.from_numpy(p).to(dev) for p in poses]
+    d_parents = [torch.from_numpy(p).to(dev) for p in parents]
+    d_idx = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_out = torch.zeros(n, dtype=torch.float64, device=dev)
+    d_all = torch.zeros(n * world, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def device_step(k):
+        f = k % N_FRAMES
+        with torch.cuda.stream(ext):
+            d_idx.copy_(d_parents[f], non_blocking=True)   # resampled parents of this frame
+            sensor.set_observation_device(d_frames[f].data_ptr())
+            sensor.loglikes_device(d_poses[f].data_ptr(), d_idx.data_ptr(), n, True, d_out.data_ptr())
+            if world > 1:  # the one exchange of the sharded evaluator: all ranks see all weights
+                dist.all_gather_into_tensor(d_all, d_out)
+
+    def sync_all():
+        sensor.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        sensor.timer_begin()
+        for k in range(steps):
+            fn(k)
+        ms = sensor.timer_end()
+        sync_all()
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # establish n slots, then warm up
+    sensor.set_observation(frames[0])
+    sensor.loglikes_poses(poses[0], np.zeros(n, dtype=np.int32), True)
+    timed(device_step, args.warmup)
+    launches0 = sensor.launch_count
+    with ClockSampler(local_rank) as clocks:
+        ms = timed(device_step, args.steps)
+    gpu_launches = int(sensor.launch_count - launches0)
+    value = n * world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers through the reference-facing call ----
+    idx_host = [p.copy() for p in parents]
+
+    def host_step(k):
+        f = k % N_FRAMES
+        idx_host[f][:] = parents[f]
+        sensor.set_observation(frames[f])
+        out = sensor.loglikes_poses(poses[f], idx_host[f], True)
+        if world > 1:
+            with torch.cuda.stream(ext):
+                d_out.copy_(torch.from_numpy(out), non_blocking=True)
+                dist.all_gather_into_tensor(d_all, d_out)
+            ext.synchronize()
+            d_all.cpu()
+
+    for k in range(args.warmup):
+        host_step(k)
+    sync_all()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        host_step(k)
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = n * world * args.steps / e2e_s
+    h2d = P * 4 + n * len(w["V"]) * 12 * 4 + n * 4
+    d2h = n * 8
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the library's stream ----
+    sensor.profile_enable(True)
+    for k in range(args.steps):
+        device_step(k)
+    sync_all()
+    prof = sensor.profile_read()
+    sensor.profile_enable(False)
+    k_ms, k_cnt = prof["update"]
+    o_ms, o_cnt = prof["observation"]
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = 8.0 * P * n                       # 4P read + 4P written per particle
+    avg_ms = k_ms / max(k_cnt, 1)
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "dbot_particle_kernel<UPDATE>", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                "avg_launch_ms": avg_ms, "launches_timed": k_cnt,
+                "kernel_share_of_step": k_ms / max(k_ms + o_ms, 1e-9),
+                "observation_kernel_avg_ms": o_ms / max(o_cnt, 1)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": describe(w, world), "fps": args.steps / (ms * 1e-3),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "fps": args.steps / e2e_s},
+            "gpu_launches": gpu_launches, "clocks": clocks.summary(), "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = 64
+        rate, cores, sec = cpu_oracle_rate(w, frames, poses, sample, reps=6)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d of the %d particles, 6 frames, %.2f s per frame"
+                                          % (sample, n, sec)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

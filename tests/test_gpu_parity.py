@@ -1,0 +1,219 @@
+"""GPU parity: libdbot_b200.so (through the C-ABI / host mirror) against the CPU oracle on the same
+seeded inputs.  Bars: rendered depth bit-exact (integer coverage + identical fp32 op order);
+log-weights within 1e-4 relative (BASELINE.json north_star); occlusion images within 2e-5."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from dbot_ros_b200 import (CameraData, DbotB200Error, ObjectModel, Parameters, RbSensorBuilder,
+                           synth)
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4   # north_star: log-weights within 1e-4 relative of the CPU reference
+OCC_TOL = 2e-5  # fp32 posterior: ex2.approx argument rounding at |t|^2 ~ 20
+
+
+def rel_err(got, want):
+    return np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0)) if len(want) else 0.0
+
+
+def make_pair(mesh, ds, max_n, K=None):
+    rows, cols = synth.resolution(ds)
+    K = synth.camera_matrix(ds) if K is None else K
+    V, T = synth.mesh_set(mesh) if isinstance(mesh, str) else mesh
+    sensor = RbSensorBuilder(ObjectModel(V, T), CameraData(K, rows, cols),
+                             Parameters(sample_count=max_n)).build()
+    orc = oracle_lib.Oracle(rows, cols, K, V, T, synth.default_parameters())
+    return sensor, orc, rows, cols, len(V)
+
+
+@pytest.mark.parametrize("mesh,ds", [("uvsphere480", 4), ("icosphere5k", 1), ("three20k", 2),
+                                     ("ico80", 8)])
+def test_render_bit_exact(mesh, ds):
+    sensor, orc, rows, cols, n_obj = make_pair(mesh, ds, 8)
+    rng = np.random.default_rng(5)
+    gt = synth.ground_truth_poses(n_obj, rng)
+    for pose in synth.particle_poses(gt, 6, rng, sigma_t=0.03, sigma_r=0.5):
+        got = sensor.render(pose)
+        want = orc.render(pose)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        assert np.isfinite(got).sum() > 0
+
+
+@pytest.mark.parametrize("mesh,ds,n", [("uvsphere480", 4, 200), ("icosphere5k", 1, 48),
+                                       ("three20k", 1, 24), ("three20k", 4, 64)])
+def test_loglikes_and_update_parity(mesh, ds, n):
+    """BASELINE configs 1, 2 and 5 at oracle-friendly particle counts"""
+    sensor, orc, rows, cols, n_obj = make_pair(mesh, ds, n)
+    rng = synth.rng_for(2)
+    gt = synth.ground_truth_poses(n_obj, rng)
+    frame = synth.make_frame(orc.render, gt, rows, cols, rng)
+    poses = synth.particle_poses(gt, n, rng)
+    sensor.set_observation(frame)
+    orc.set_observation(frame)
+    ia = np.zeros(n, dtype=np.int32)
+    ib = np.zeros(n, dtype=np.int32)
+    # update=False must not touch state
+    got = sensor.loglikes_poses(poses, ia, update=False)
+    want = orc.loglikes_poses(poses, ib, update=False)
+    assert rel_err(got, want) < REL_TOL
+    assert sensor.n_slots == 1 and np.all(ia == 0)
+    again = sensor.loglikes_poses(poses, ia, update=False)
+    assert np.array_equal(got, again)  # deterministic reduction
+    got = sensor.loglikes_poses(poses, ia, update=True)
+    want = orc.loglikes_poses(poses, ib, update=True)
+    assert rel_err(got, want) < REL_TOL
+    assert np.array_equal(ia, np.arange(n)) and np.array_equal(ib, ia)
+    assert sensor.n_slots == n == orc.n_slots
+    for slot in (0, n // 2, n - 1):
+        assert np.max(np.abs(sensor.occlusion(slot) - orc.occlusion(slot))) < OCC_TOL
+
+
+def test_multi_frame_with_resampling():
+    """5 frames; parents drawn at random each frame (what the filter's resampling does to
+    `indices`); log-weights and occlusion state must track the oracle frame after frame."""
+    n = 96
+    sensor, orc, rows, cols, n_obj = make_pair("uvsphere480", 4, n)
+    rng = synth.rng_for(1)
+    gt = synth.ground_truth_poses(n_obj, rng)
+    ia = np.zeros(n, dtype=np.int32)
+    for f in range(5):
+        frame = synth.make_frame(orc.render, gt, rows, cols, rng)
+        poses = synth.particle_poses(gt, n, rng)
+        sensor.set_observation(frame)
+        orc.set_observation(frame)
+        assert abs(sensor.observation_time - orc.observation_time) < 1e-12
+        if f > 0:
+            ia = rng.integers(0, n, size=n).astype(np.int32)
+        ib = ia.copy()
+        if f == 2:  # a frame with an extra non-updating call first (second sampling block)
+            g0 = sensor.loglikes_poses(poses, ia, update=False)
+            w0 = orc.loglikes_poses(poses, ib, update=False)
+            assert rel_err(g0, w0) < REL_TOL
+        got = sensor.loglikes_poses(poses, ia, update=True)
+        want = orc.loglikes_poses(poses, ib, update=True)
+        assert rel_err(got, want) < REL_TOL, "frame %d" % f
+        for slot in (0, n - 1):
+            assert np.max(np.abs(sensor.occlusion(slot) - orc.occlusion(slot))) < 2 * OCC_TOL
+    # occlusion read-back between frames is "as of the current observation time"
+    frame = synth.make_frame(orc.render, gt, rows, cols, rng)
+    sensor.set_observation(frame)
+    orc.set_observation(frame)
+    assert np.max(np.abs(sensor.occlusion(3) - orc.occlusion(3))) < 2 * OCC_TOL
+    sensor.reset()
+    orc.reset()
+    assert sensor.n_slots == 1 and sensor.observation_time == 0.0
+    assert np.allclose(sensor.occlusion(0), 0.1)
+
+
+def test_multi_chunk_mesh_and_big_window():
+    """icosphere level 5 (10242 vertices / 20480 triangles -> several TMA-staged chunks) held
+    25 cm from the camera: the window covers most of the frame -> several z-tile bands."""
+    V, T = synth.icosphere(5, radius=0.1, seed=9)
+    sensor, orc, rows, cols, _ = make_pair(([V], [T]), 1, 8)
+    rng = np.random.default_rng(11)
+    gt = [(synth.rodrigues([0.3, -0.2, 0.9]), np.array([0.02, -0.01, 0.25]))]
+    pose = synth.pack_pose(*gt[0])
+    got = sensor.render(pose)
+    want = orc.render(pose)
+    assert np.isfinite(want).sum() > 0.4 * rows * cols
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    frame = synth.make_frame(orc.render, gt, rows, cols, rng)
+    poses = synth.particle_poses(gt, 8, rng)
+    sensor.set_observation(frame)
+    orc.set_observation(frame)
+    ia = np.zeros(8, dtype=np.int32)
+    ib = np.zeros(8, dtype=np.int32)
+    assert rel_err(sensor.loglikes_poses(poses, ia, True), orc.loglikes_poses(poses, ib, True)) < REL_TOL
+    assert np.max(np.abs(sensor.occlusion(5) - orc.occlusion(5))) < OCC_TOL
+
+
+def test_edge_cases():
+    n = 16
+    sensor, orc, rows, cols, _ = make_pair("ico80", 4, n)
+    rng = np.random.default_rng(3)
+    gt = [(np.eye(3), np.array([0.0, 0.0, 0.8]))]
+    frame = synth.make_frame(orc.render, gt, rows, cols, rng)
+    sensor.set_observation(frame)
+    orc.set_observation(frame)
+    poses = synth.particle_poses(gt, n, rng)
+    # off-screen, behind the camera, straddling the image border, straddling z = 0
+    poses[0, 0, 9:] = (5.0, 0.0, 0.8)
+    poses[1, 0, 9:] = (0.0, 0.0, -0.8)
+    poses[2, 0, 9:] = (-0.42, 0.3, 0.8)
+    poses[3, 0, 9:] = (0.0, 0.0, 0.05)
+    ia = np.zeros(n, dtype=np.int32)
+    ib = np.zeros(n, dtype=np.int32)
+    got = sensor.loglikes_poses(poses, ia, False)
+    want = orc.loglikes_poses(poses, ib, False)
+    assert got[0] == 0.0 and got[1] == 0.0
+    assert rel_err(got, want) < REL_TOL
+    # empty call
+    e = np.zeros(0, dtype=np.int32)
+    assert sensor.loglikes_poses(np.zeros((0, 1, 12), np.float32), e, False).size == 0
+    # all-NaN frame: every pixel is "no data" -> log-weight 0, occlusion only propagates
+    sensor.set_observation(np.full((rows, cols), np.nan, np.float32))
+    orc.set_observation(np.full((rows, cols), np.nan, np.float32))
+    got = sensor.loglikes_poses(poses, ia, True)
+    want = orc.loglikes_poses(poses, ib, True)
+    assert np.all(got == 0.0) and np.all(want == 0.0)
+    assert np.max(np.abs(sensor.occlusion(4) - orc.occlusion(4))) < OCC_TOL
+    # errors: too many particles, parent slot out of range (mirrors dbot's GPU model exceptions)
+    with pytest.raises(DbotB200Error):
+        sensor.loglikes_poses(np.zeros((n + 1, 1, 12), np.float32), np.zeros(n + 1, np.int32), False)
+    bad = np.full(n, n, dtype=np.int32)
+    with pytest.raises(DbotB200Error):
+        sensor.loglikes_poses(poses, bad, False)
+
+
+def test_odd_resolution_pitch():
+    """cols not a multiple of 4 -> padded state pitch"""
+    rows, cols = 61, 83
+    K = np.array([[70.0, 0.3, 41.0], [0, 71.0, 30.0], [0, 0, 1]])
+    V, T = synth.mesh_set("ico80")
+    sensor = RbSensorBuilder(ObjectModel(V, T), CameraData(K, rows, cols), Parameters(sample_count=8)).build()
+    orc = oracle_lib.Oracle(rows, cols, K, V, T, synth.default_parameters())
+    rng = np.random.default_rng(8)
+    gt = [(synth.rodrigues([0.1, 0.2, 0.3]), np.array([0.01, 0.0, 0.6]))]
+    frame = synth.make_frame(orc.render, gt, rows, cols, rng)
+    poses = synth.particle_poses(gt, 8, rng)
+    for s in (sensor, orc):
+        s.set_observation(frame)
+    ia = np.zeros(8, dtype=np.int32)
+    ib = np.zeros(8, dtype=np.int32)
+    assert np.array_equal(sensor.render(poses[0]).view(np.uint32), orc.render(poses[0]).view(np.uint32))
+    assert rel_err(sensor.loglikes_poses(poses, ia, True), orc.loglikes_poses(poses, ib, True)) < REL_TOL
+    assert np.max(np.abs(sensor.occlusion(7) - orc.occlusion(7))) < OCC_TOL
+
+
+def test_full_size_properties():
+    """BASELINE config 2 at full size (1000 particles, 640x480, 5120 triangles): properties that
+    need no oracle -- shard invariance (what the multi-GPU split relies on), permutation
+    equivariance, determinism -- plus an oracle spot check on 16 of the particles."""
+    n = 1000
+    sensor, orc, rows, cols, n_obj = make_pair("icosphere5k", 1, n)
+    rng = synth.rng_for(2)
+    gt = synth.ground_truth_poses(n_obj, rng)
+    frame = synth.make_frame(sensor.render, gt, rows, cols, rng)
+    poses = synth.particle_poses(gt, n, rng)
+    sensor.set_observation(frame)
+    idx = np.zeros(n, dtype=np.int32)
+    whole = sensor.loglikes_poses(poses, idx, False)
+    halves = np.concatenate([sensor.loglikes_poses(poses[:500], idx[:500].copy(), False),
+                             sensor.loglikes_poses(poses[500:], idx[500:].copy(), False)])
+    assert np.array_equal(whole, halves)
+    perm = rng.permutation(n)
+    assert np.array_equal(sensor.loglikes_poses(poses[perm], idx, False), whole[perm])
+    upd = sensor.loglikes_poses(poses, idx, True)
+    assert np.array_equal(upd, whole)            # update does not change the weights of its call
+    assert np.array_equal(idx, np.arange(n))
+    # after the update with dt = 0 the second evaluation uses the posterior occlusion
+    orc.set_observation(frame)
+    pick = rng.choice(n, 16, replace=False)
+    io = np.zeros(16, dtype=np.int32)
+    want = orc.loglikes_poses(poses[pick], io, True)
+    assert rel_err(whole[pick], want) < REL_TOL
+    second = sensor.loglikes_poses(poses[pick], pick.astype(np.int32), False)
+    want2 = orc.loglikes_poses(poses[pick], np.arange(16, dtype=np.int32), False)
+    assert rel_err(second, want2) < REL_TOL

@@ -1,0 +1,185 @@
+"""Pins the CPU oracle (parity is otherwise unpinned: the reference tree has no tests, golden
+vectors or fixtures for this path -- SURVEY.md section 4 / 8c): closed-form known answers from
+SURVEY.md Appendix A, analytic raster cases, and an independent numpy re-derivation."""
+import numpy as np
+import pytest
+from scipy import integrate
+
+import np_model
+import oracle_lib
+from dbot_ros_b200 import synth
+
+PRM = synth.default_parameters()
+
+
+def small_oracle(mesh="ico80", ds=8, **kw):
+    rows, cols = synth.resolution(ds)
+    V, T = synth.mesh_set(mesh)
+    return oracle_lib.Oracle(rows, cols, synth.camera_matrix(ds), V, T, PRM, **kw), rows, cols, V, T
+
+
+def test_propagation_known_answers():
+    o, *_ = small_oracle()
+    f = o.lib.oracle_propagate
+    assert abs(f(o.h, 0.0, 1.0) - PRM["p_occluded_visible"]) < 1e-15
+    assert abs(f(o.h, 1.0, 1.0) - PRM["p_occluded_occluded"]) < 1e-15
+    assert abs(f(o.h, 0.37, 0.0) - 0.37) < 1e-15
+    # semigroup: 30 steps of 1/30 s == one step of 1 s
+    x = 0.25
+    for _ in range(30):
+        x = f(o.h, x, 1.0 / 30.0)
+    assert abs(x - f(o.h, 0.25, 1.0)) < 1e-13
+    # stationary point
+    c = PRM["p_occluded_occluded"] - PRM["p_occluded_visible"]
+    fix = PRM["p_occluded_visible"] / (1 - c)
+    assert abs(f(o.h, fix, 0.7) - fix) < 1e-14
+
+
+def test_pixel_density_known_answers():
+    o, *_ = small_oracle()
+    w, D, ms, sf = PRM["tail_weight"], PRM["max_depth"], PRM["model_sigma"], PRM["sigma_factor"]
+    lam = np.log(2.0) / PRM["half_life_depth"]
+    y, d = 0.62, 0.80
+    s = ms + sf * y * y
+    # visible: tail + Gaussian around the prediction, sigma from the OBSERVATION
+    want = w / D + (1 - w) * np.exp(-0.5 * ((d - y) / s) ** 2) / (np.sqrt(2 * np.pi) * s)
+    assert abs(o.lib.oracle_p_visible(o.h, y, d) - want) < 1e-15
+    assert abs(o.lib.oracle_p_visible(o.h, y, np.inf) - w / D) < 1e-18
+    # occluded: truncated exponential on [0,d] convolved with the Gaussian, by quadrature
+    def integrand(c):
+        return lam * np.exp(-lam * c) / (1 - np.exp(-lam * d)) * \
+            np.exp(-0.5 * ((y - c) / s) ** 2) / (np.sqrt(2 * np.pi) * s)
+    num, _ = integrate.quad(integrand, 0, d, points=[y], epsabs=1e-14, epsrel=1e-13)
+    got = o.lib.oracle_p_occluded(o.h, y, d)
+    assert abs(got - (w / D + (1 - w) * num)) < 1e-11
+    # d -> inf limit
+    assert abs(o.lib.oracle_p_occluded(o.h, y, 60.0) - o.lib.oracle_p_occluded_inf(o.h, y)) < 1e-12
+    assert o.lib.oracle_p_occluded(o.h, y, np.inf) == o.lib.oracle_p_occluded_inf(o.h, y)
+    # numpy re-derivation agrees
+    for yy, dd in [(0.5, 0.5), (0.9, 0.4), (0.4, 0.9), (1.5, 1.49), (3.0, 0.2)]:
+        assert np.isclose(o.lib.oracle_p_visible(o.h, yy, dd), np_model.p_visible(yy, dd, w, D, ms, sf), rtol=1e-13)
+        assert np.isclose(o.lib.oracle_p_occluded(o.h, yy, dd), np_model.p_occluded(yy, dd, w, D, ms, sf, lam), rtol=1e-12)
+
+
+def quad_mesh(half=0.1):
+    V = np.array([[-half, -half, 0], [half, -half, 0], [half, half, 0], [-half, half, 0]], np.float32)
+    T = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    return [V], [T]
+
+
+def test_fronto_parallel_quad_analytic():
+    """quad of half-size 0.1 m at z = 0.5 m, K = [[100,0,40],[0,100,30]]: covers columns 20..60 and
+    rows 10..50 inclusive (closed edges, integer sample points), depth exactly 0.5 everywhere."""
+    K = np.array([[100.0, 0, 40.0], [0, 100.0, 30.0], [0, 0, 1]])
+    V, T = quad_mesh()
+    o = oracle_lib.Oracle(60, 80, K, V, T, PRM)
+    pose = synth.pack_pose(np.eye(3), [0, 0, 0.5])
+    d = o.render(pose)
+    cov = np.isfinite(d)
+    assert cov.sum() == 41 * 41
+    assert cov[10:51, 20:61].all() and not cov[9, :].any() and not cov[:, 19].any()
+    assert np.all(d[cov] == np.float32(0.5))
+    # whole-pixel translation (0.01 m * 100 px/m / 0.5 m = 2 px) shifts coverage exactly
+    d2 = o.render(synth.pack_pose(np.eye(3), [0.01, -0.005, 0.5]))
+    assert np.array_equal(np.isfinite(d2)[9:50, 22:63], cov[10:51, 20:61])
+    assert np.isfinite(d2).sum() == 41 * 41
+    # a shared diagonal is not double counted and leaves no crack
+    one = oracle_lib.Oracle(60, 80, K, V, [T[0][:1]], PRM).render(pose)
+    two = oracle_lib.Oracle(60, 80, K, V, [T[0][1:]], PRM).render(pose)
+    assert np.array_equal(np.isfinite(one) | np.isfinite(two), cov)
+    # tilted quad: depth follows the plane (z = 0.5 + x * tan) to float precision
+    R = synth.rodrigues([0, 0.3, 0])
+    d3 = o.render(synth.pack_pose(R, [0, 0, 0.5]))
+    rr, cc = np.nonzero(np.isfinite(d3))
+    n = R[:, 2]
+    ray = np.stack([(cc - 40.0) / 100.0, (rr - 30.0) / 100.0, np.ones(len(rr))], 1)
+    z_true = (n @ np.array([0, 0, 0.5])) / (ray @ n)
+    assert np.max(np.abs(d3[rr, cc] - z_true)) < 2e-6
+    # two quads at different depths: min z wins regardless of object order
+    V2 = [V[0], V[0]]
+    T2 = [T[0], T[0]]
+    oo = oracle_lib.Oracle(60, 80, K, V2, T2, PRM)
+    pa, pb = synth.pack_pose(np.eye(3), [0, 0, 0.5]), synth.pack_pose(np.eye(3), [0.05, 0, 0.4])
+    dz = oo.render(np.stack([pa, pb]))
+    dz2 = oo.render(np.stack([pb, pa]))
+    assert np.array_equal(dz, dz2)
+    assert dz[30, 40] == np.float32(0.4) and dz[30, 21] == np.float32(0.5)
+
+
+@pytest.mark.parametrize("mesh,ds", [("ico80", 8), ("uvsphere480", 4)])
+def test_oracle_vs_numpy_rederivation(mesh, ds):
+    o, rows, cols, V, T = small_oracle(mesh, ds, eager=0)
+    rng = np.random.default_rng(4)
+    gt = synth.ground_truth_poses(1, rng)
+    frame = synth.make_frame(o.render, gt, rows, cols, rng)
+    poses = synth.particle_poses(gt, 3, rng, sigma_t=0.02, sigma_r=0.3)
+    o.set_observation(frame)
+    idx = np.zeros(3, dtype=np.int32)
+    L = o.loglikes_poses(poses, idx, True)
+    for i in range(3):
+        d_np = np_model.render(synth.camera_matrix(ds), rows, cols, V, T, poses[i])
+        d_or = o.render(poses[i])
+        assert np.array_equal(np.isfinite(d_np), np.isfinite(d_or))      # coverage: exact
+        m = np.isfinite(d_or)
+        assert np.max(np.abs(d_np[m] - d_or[m]) / d_or[m]) < 1e-6          # depth: fp32 rounding
+        Ln, post = np_model.loglike(d_or, frame, np.full((rows, cols), 0.1, np.float32), 1.0 / 30.0, PRM)
+        assert abs(Ln - L[i]) < 1e-9 * max(1.0, abs(L[i]))
+        assert np.max(np.abs(o.occlusion(i) - post)) < 1e-6
+
+
+def test_state_semantics():
+    """SURVEY.md section 8b 'semantics that must match'"""
+    o, rows, cols, V, T = small_oracle()
+    rng = np.random.default_rng(7)
+    gt = synth.ground_truth_poses(1, rng)
+    frame = synth.make_frame(o.render, gt, rows, cols, rng)
+    poses = synth.particle_poses(gt, 5, rng)
+    o.set_observation(frame)
+    assert abs(o.observation_time - 1.0 / 30.0) < 1e-15
+    idx = np.zeros(5, dtype=np.int32)
+    a = o.loglikes_poses(poses, idx, False)
+    assert o.n_slots == 1 and np.all(idx == 0)
+    b = o.loglikes_poses(poses, idx, False)
+    assert np.array_equal(a, b)                       # update=false does not mutate
+    c = o.loglikes_poses(poses, idx, True)
+    assert np.array_equal(a, c) and o.n_slots == 5 and np.array_equal(idx, np.arange(5))
+    # NaN pixels contribute nothing
+    o.reset()
+    f2 = frame.copy()
+    f2[:] = np.nan
+    o.set_observation(f2)
+    assert np.all(o.loglikes_poses(poses, np.zeros(5, np.int32), False) == 0.0)
+    # child slots copy the parent named by indices
+    o.reset()
+    o.set_observation(frame)
+    o.loglikes_poses(poses, np.zeros(5, np.int32), True)
+    o.set_observation(frame)
+    par = np.array([3, 3, 0, 1, 1], dtype=np.int32)
+    before = [o.occlusion(s) for s in range(5)]
+    far = poses.copy()
+    far[:, 0, 9:] = (9.0, 9.0, 1.0)                   # nothing rendered: children = propagated parents
+    o.loglikes_poses(far, par, True)
+    for child, parent in enumerate([3, 3, 0, 1, 1]):
+        assert np.max(np.abs(o.occlusion(child) - before[parent])) < 1e-6
+
+
+def test_lazy_and_eager_oracle_agree():
+    """dbot's CPU model time-stamps pixels (lazy); its GPU evaluator propagates whole images on
+    update (eager).  The propagation is a semigroup, so both give the same numbers to rounding."""
+    res = []
+    for eager in (0, 1):
+        o, rows, cols, V, T = small_oracle("uvsphere480", 4, eager=eager)
+        rng = np.random.default_rng(12)
+        gt = synth.ground_truth_poses(1, rng)
+        idx = np.zeros(12, dtype=np.int32)
+        Ls = []
+        for f in range(4):
+            frame = synth.make_frame(o.render, gt, rows, cols, rng)
+            poses = synth.particle_poses(gt, 12, rng)
+            o.set_observation(frame)
+            if f:
+                idx = rng.integers(0, 12, 12).astype(np.int32)
+            Ls.append(o.loglikes_poses(poses, idx, True))
+        res.append((np.concatenate(Ls), o.occlusion(5)))
+    assert np.max(np.abs(res[0][0] - res[1][0]) / np.maximum(1, np.abs(res[0][0]))) < 1e-6
+    assert np.max(np.abs(res[0][1] - res[1][1])) < 1e-6
