@@ -33,10 +33,14 @@
 #include <unordered_map>
 #include <vector>
 
-#define DBOT_NT 512              /* threads per CTA */
+#define DBOT_CW 16                 /* compute warps per CTA */
+#define DBOT_CT (DBOT_CW * 32)     /* compute threads */
+#define DBOT_SW 4                  /* streaming warps per CTA (update launches only) */
+#define DBOT_ST (DBOT_SW * 32)
+#define DBOT_STREAM_UNROLL 8       /* 256-bit loads in flight per streaming thread */
 #define DBOT_CHUNK_MAX_VERTS 3072
 #define DBOT_CHUNK_MAX_TRIS 6144
-#define DBOT_STREAM_UNROLL 4
+#define DBOT_FULL 0xffffffffu
 
 enum
 {
@@ -54,7 +58,7 @@ struct dbot_chunk
 
 struct dbot_kparams
 {
-    int rows, cols, pitch; /* pitch: floats per state / table row, multiple of 4 */
+    int rows, cols, pitch; /* pitch: floats per state / table row, multiple of 8 */
     int n_obj, n_chunks;
     int n, n_slots;
     dbot_camera K;
@@ -71,12 +75,13 @@ struct dbot_kparams
     float* depth_out;       /* render: [rows*cols] */
     int* err_flag;
     /* shared-memory carve-up (bytes from the dynamic smem base) */
-    uint32_t off_tri, off_vert, off_X, off_Y, off_x, off_y, off_z, off_zt;
-    uint32_t zcap;          /* z tile capacity in pixels */
+    uint32_t off_tri, off_v4, off_Y, off_wt;
+    uint32_t wcap;          /* inverse-depth tile capacity in pixels */
 };
 
 /* ------------------------------------------------------------------------------------------ */
-/* PTX wrappers: mbarrier + TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP)                     */
+/* PTX wrappers: mbarrier, TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP), named barriers,     */
+/* 256-bit streaming loads / stores (SASS LDG.256 / STG.256, new with sm_100)                   */
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -84,6 +89,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p)
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
@@ -91,6 +99,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                  "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
                                             uint64_t* bar)
@@ -113,6 +125,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "DONE:\n"
         "}" ::"r"(smem_u32(bar)),
         "r"(parity)
+        : "memory");
+}
+/* barrier among the compute warps only (the streaming warps never take part) */
+__device__ __forceinline__ void compute_sync()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(DBOT_CT) : "memory");
+}
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8])
+{
+    asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]),
+                   "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256_stream(float* p, const float (&v)[8])
+{
+    asm volatile(
+        "st.global.L1::no_allocate.L2::evict_first.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
         : "memory");
 }
 
@@ -155,46 +186,231 @@ __global__ void dbot_fill_kernel(float* __restrict__ dst, size_t n, float v)
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* K2: fused transform + raster + likelihood (+ occlusion stream) kernel                       */
+/* raster: the triangles of one staged chunk into the inverse-depth tile covering rows
+ * [row0,row1] x columns [col0,col1].  A warp takes 32 triangles at a time: every lane sets its
+ * triangle up (convergent), then walks its own pixel box with incremental int32 edge functions;
+ * triangles whose box is far larger than the batch average (or that need int64 edge functions)
+ * are instead walked by the whole warp, 8 x 4 pixels per step.                                 */
+__device__ __forceinline__ void dbot_zmax(uint32_t* p, uint32_t v)
+{
+    if (v > *p) atomicMax(p, v); /* plain read first: fragments that lose the test cost no atomic */
+}
+
+__device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s_tri, int ntri,
+                                                  const float4* __restrict__ s_v4,
+                                                  const int* __restrict__ s_Y, const dbot_camera& K,
+                                                  uint32_t* s_wt, int row0, int row1, int col0,
+                                                  int col1, int warp, int lane)
+{
+    const int ww = col1 - col0 + 1;
+    for (int base = warp * 32; base < ntri; base += DBOT_CW * 32)
+    {
+        const int t = base + lane;
+        dbot_tri s;
+        bool ok = false;
+        if (t < ntri)
+        {
+            const int ia = s_tri[3 * t], ib = s_tri[3 * t + 1], ic = s_tri[3 * t + 2];
+            const float4 pa = s_v4[ia], pb = s_v4[ib], pc = s_v4[ic];
+            dbot_vertex a, b, c;
+            a.x = pa.x; a.y = pa.y; a.z = pa.z; a.X = __float_as_int(pa.w); a.Y = s_Y[ia];
+            b.x = pb.x; b.y = pb.y; b.z = pb.z; b.X = __float_as_int(pb.w); b.Y = s_Y[ib];
+            c.x = pc.x; c.y = pc.y; c.z = pc.z; c.X = __float_as_int(pc.w); c.Y = s_Y[ic];
+            ok = dbot_setup_triangle(a, b, c, K, row0, row1, col0, col1, s);
+        }
+        const int area = ok ? (s.cmax - s.cmin + 1) * (s.rmax - s.rmin + 1) : 0;
+        int tot = area;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(DBOT_FULL, tot, off);
+        const int thresh = max(64, tot >> 3); /* 4 x the batch mean */
+        const bool big = ok && (area > thresh || !s.small);
+
+        if (ok && !big)
+        {
+            int e0c = -(s.Yb - s.Ya) * DBOT_SUBPIX, e0r = (s.Xb - s.Xa) * DBOT_SUBPIX;
+            int e1c = -(s.Yc - s.Yb) * DBOT_SUBPIX, e1r = (s.Xc - s.Xb) * DBOT_SUBPIX;
+            int e2c = -(s.Ya - s.Yc) * DBOT_SUBPIX, e2r = (s.Xa - s.Xc) * DBOT_SUBPIX;
+            const int px0 = s.cmin * DBOT_SUBPIX, py0 = s.rmin * DBOT_SUBPIX;
+            int e0 = (s.Xb - s.Xa) * (py0 - s.Ya) - (s.Yb - s.Ya) * (px0 - s.Xa);
+            int e1 = (s.Xc - s.Xb) * (py0 - s.Yb) - (s.Yc - s.Yb) * (px0 - s.Xb);
+            int e2 = (s.Xa - s.Xc) * (py0 - s.Yc) - (s.Ya - s.Yc) * (px0 - s.Xc);
+            if (s.flip)
+            {
+                e0 = -e0; e1 = -e1; e2 = -e2;
+                e0c = -e0c; e1c = -e1c; e2c = -e2c;
+                e0r = -e0r; e1r = -e1r; e2r = -e2r;
+            }
+            const float fc0 = (float)s.cmin;
+            float fr = (float)s.rmin;
+            uint32_t* wrow = s_wt + (s.rmin - row0) * ww - col0;
+            for (int r = s.rmin; r <= s.rmax; ++r)
+            {
+                int a0 = e0, a1 = e1, a2 = e2;
+                float fc = fc0;
+                const float wr = dbot_fmaf(s.m1, fr, s.m2);
+                for (int c = s.cmin; c <= s.cmax; ++c)
+                {
+                    if ((a0 | a1 | a2) >= 0)
+                    {
+                        const float w = dbot_fmaf(s.m0, fc, wr);
+                        dbot_zmax(wrow + c, dbot_f2u(fminf(fmaxf(w, s.wlo), s.whi)));
+                    }
+                    a0 += e0c; a1 += e1c; a2 += e2c;
+                    fc = dbot_add(fc, 1.0f);
+                }
+                e0 += e0r; e1 += e1r; e2 += e2r;
+                fr = dbot_add(fr, 1.0f);
+                wrow += ww;
+            }
+        }
+        __syncwarp();
+
+        unsigned m = __ballot_sync(DBOT_FULL, big);
+        while (m)
+        {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            dbot_tri q;
+            q.Xa = __shfl_sync(DBOT_FULL, s.Xa, j); q.Ya = __shfl_sync(DBOT_FULL, s.Ya, j);
+            q.Xb = __shfl_sync(DBOT_FULL, s.Xb, j); q.Yb = __shfl_sync(DBOT_FULL, s.Yb, j);
+            q.Xc = __shfl_sync(DBOT_FULL, s.Xc, j); q.Yc = __shfl_sync(DBOT_FULL, s.Yc, j);
+            q.cmin = __shfl_sync(DBOT_FULL, s.cmin, j); q.cmax = __shfl_sync(DBOT_FULL, s.cmax, j);
+            q.rmin = __shfl_sync(DBOT_FULL, s.rmin, j); q.rmax = __shfl_sync(DBOT_FULL, s.rmax, j);
+            q.flip = __shfl_sync(DBOT_FULL, s.flip, j);
+            q.small = 0;
+            q.m0 = __shfl_sync(DBOT_FULL, s.m0, j); q.m1 = __shfl_sync(DBOT_FULL, s.m1, j);
+            q.m2 = __shfl_sync(DBOT_FULL, s.m2, j);
+            q.wlo = __shfl_sync(DBOT_FULL, s.wlo, j); q.whi = __shfl_sync(DBOT_FULL, s.whi, j);
+            const int dc = lane & 7, dr = lane >> 3;
+            for (int r0 = q.rmin; r0 <= q.rmax; r0 += 4)
+            {
+                const int r = r0 + dr;
+                for (int c0 = q.cmin; c0 <= q.cmax; c0 += 8)
+                {
+                    const int c = c0 + dc;
+                    if (r <= q.rmax && c <= q.cmax && dbot_covers(q, c, r))
+                        dbot_zmax(s_wt + (r - row0) * ww + (c - col0),
+                                  dbot_fragment_w(q, (float)c, (float)r));
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* K2: fused transform + raster + likelihood (+ occlusion stream) kernel.
+ * Warp roles: warps [0, DBOT_CW) compute; in update launches warps [DBOT_CW, DBOT_CW+DBOT_SW)
+ * stream the parent's propagated occlusion image into the child's slot while the compute warps
+ * transform and rasterise the same particle; the compute warps then overwrite the covered
+ * pixels with the posterior.  Hand-off through two mbarriers (image copied / copy consumed). */
 template <int MODE>
-__global__ void __launch_bounds__(DBOT_NT, 1) dbot_particle_kernel(const __grid_constant__ dbot_kparams p)
+__global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST : 0), 1)
+    dbot_particle_kernel(const __grid_constant__ dbot_kparams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar;      /* TMA mesh staging */
+    __shared__ __align__(8) uint64_t s_copied;   /* streaming warps -> compute warps */
+    __shared__ __align__(8) uint64_t s_consumed; /* compute warps -> streaming warps */
     __shared__ int s_bb[4];
-    __shared__ double s_red[DBOT_NT / 32];
-
-    uint16_t* s_tri = (uint16_t*)(smem + p.off_tri);
-    float* s_vert = (float*)(smem + p.off_vert);
-    int* s_X = (int*)(smem + p.off_X);
-    int* s_Y = (int*)(smem + p.off_Y);
-    float* s_x = (float*)(smem + p.off_x);
-    float* s_y = (float*)(smem + p.off_y);
-    float* s_z = (float*)(smem + p.off_z);
-    uint32_t* s_zt = (uint32_t*)(smem + p.off_zt);
+    __shared__ double s_red[DBOT_CW];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) mbar_init(&s_bar, 1);
+    if (tid == 0)
+    {
+        mbar_init(&s_bar, 1);
+        mbar_init(&s_copied, DBOT_ST);
+        mbar_init(&s_consumed, DBOT_CW);
+        mbar_fence_init();
+    }
     __syncthreads();
+
+    /* ================= streaming warps (update launches only) ================= */
+    if (MODE == DBOT_MODE_UPDATE && warp >= DBOT_CW)
+    {
+        const int sl = tid - DBOT_CT;
+        const int n8 = (int)(p.slot_stride >> 3);
+        const float A = p.M.prop_a, B = p.M.prop_b;
+        uint32_t k = 0;
+        for (int i = blockIdx.x; i < p.n; i += gridDim.x)
+        {
+            const int slot = p.indices[i];
+            if (slot < 0 || slot >= p.n_slots) continue;
+            /* at most one particle ahead of the compute warps */
+            if (k > 0) mbar_wait(&s_consumed, (k - 1) & 1u);
+            const float* in = p.occ_in + (size_t)slot * p.slot_stride;
+            float* out = p.occ_out + (size_t)i * p.slot_stride;
+            for (int base = sl; base < n8; base += DBOT_ST * DBOT_STREAM_UNROLL)
+            {
+                float v[DBOT_STREAM_UNROLL][8];
+#pragma unroll
+                for (int u = 0; u < DBOT_STREAM_UNROLL; ++u)
+                {
+                    const int q = base + u * DBOT_ST;
+                    if (q < n8) ldg256(in + ((size_t)q << 3), v[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < DBOT_STREAM_UNROLL; ++u)
+                {
+                    const int q = base + u * DBOT_ST;
+                    if (q < n8)
+                    {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[u][e] = dbot_fmaf(A, v[u][e], B);
+                        stg256_stream(out + ((size_t)q << 3), v[u]);
+                    }
+                }
+            }
+            mbar_arrive(&s_copied);
+            ++k;
+        }
+        return;
+    }
+
+    /* ================= compute warps ================= */
+    uint16_t* s_tri = (uint16_t*)(smem + p.off_tri);
+    float4* s_v4 = (float4*)(smem + p.off_v4);
+    int* s_Y = (int*)(smem + p.off_Y);
+    uint32_t* s_wt = (uint32_t*)(smem + p.off_wt);
     uint32_t parity = 0;
     int staged = -1;
+    uint32_t k = 0;
 
-    /* TMA-stage one mesh chunk: one thread arms the mbarrier with the byte count and issues
-     * two bulk copies (vertices, indices); everybody waits on the barrier phase. */
+    /* TMA-stage the triangle list of one mesh chunk: one thread arms the mbarrier with the
+     * byte count and issues the bulk copy; every compute thread waits on the barrier phase. */
     auto stage_chunk = [&](int c) {
         if (staged == c) return;
-        __syncthreads(); /* all readers of the previous chunk are done */
+        compute_sync(); /* all readers of the previous chunk are done */
         if (tid == 0)
         {
             const dbot_chunk ch = p.chunks[c];
-            mbar_expect_tx(&s_bar, ch.vert_bytes + ch.tri_bytes);
-            tma_load_1d(s_vert, p.mesh + ch.vert_off, ch.vert_bytes, &s_bar);
+            mbar_expect_tx(&s_bar, ch.tri_bytes);
             tma_load_1d(s_tri, p.mesh + ch.tri_off, ch.tri_bytes, &s_bar);
         }
         mbar_wait(&s_bar, parity);
         parity ^= 1u;
         staged = c;
+    };
+    /* v' = R v + t, projection and snapping of one chunk's vertices into shared memory */
+    auto transform_chunk = [&](const dbot_chunk& ch, const float* pose_g, int& mnx, int& mxx,
+                               int& mny, int& mxy) {
+        float pose[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) pose[e] = __ldg(pose_g + e);
+        const float4* vg = reinterpret_cast<const float4*>(p.mesh + ch.vert_off);
+        for (int v = tid; v < ch.n_verts; v += DBOT_CT)
+        {
+            const float4 o = __ldg(vg + v);
+            const dbot_vertex t = dbot_transform_vertex(o.x, o.y, o.z, pose, p.K);
+            s_v4[v] = make_float4(t.x, t.y, t.z, __int_as_float(t.X));
+            s_Y[v] = t.Y;
+            if (t.X != DBOT_VERT_INVALID)
+            {
+                mnx = min(mnx, t.X); mxx = max(mxx, t.X);
+                mny = min(mny, t.Y); mxy = max(mxy, t.Y);
+            }
+        }
     };
 
     for (int i = blockIdx.x; i < p.n; i += gridDim.x)
@@ -222,29 +438,28 @@ __global__ void __launch_bounds__(DBOT_NT, 1) dbot_particle_kernel(const __grid_
         {
             s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN;
         }
-        __syncthreads(); /* also fences the previous particle's use of shared memory */
-        dbot_bbox bb = {INT_MAX, INT_MIN, INT_MAX, INT_MIN};
+        compute_sync(); /* also fences the previous particle's use of shared memory */
+        int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
         for (int c = 0; c < p.n_chunks; ++c)
         {
-            stage_chunk(c);
+            if (c > 0) compute_sync(); /* multi-chunk: only the bounding box survives this pass */
             const dbot_chunk ch = p.chunks[c];
-            dbot_transform_vertices(s_vert, ch.n_verts, pose + 12 * ch.obj, p.K, s_X, s_Y, s_x, s_y,
-                                    s_z, tid, DBOT_NT, bb);
+            transform_chunk(ch, pose + 12 * ch.obj, mnx, mxx, mny, mxy);
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1)
         {
-            bb.min_x = min(bb.min_x, __shfl_xor_sync(0xffffffffu, bb.min_x, off));
-            bb.max_x = max(bb.max_x, __shfl_xor_sync(0xffffffffu, bb.max_x, off));
-            bb.min_y = min(bb.min_y, __shfl_xor_sync(0xffffffffu, bb.min_y, off));
-            bb.max_y = max(bb.max_y, __shfl_xor_sync(0xffffffffu, bb.max_y, off));
+            mnx = min(mnx, __shfl_xor_sync(DBOT_FULL, mnx, off));
+            mxx = max(mxx, __shfl_xor_sync(DBOT_FULL, mxx, off));
+            mny = min(mny, __shfl_xor_sync(DBOT_FULL, mny, off));
+            mxy = max(mxy, __shfl_xor_sync(DBOT_FULL, mxy, off));
         }
         if (lane == 0)
         {
-            atomicMin(&s_bb[0], bb.min_x); atomicMax(&s_bb[1], bb.max_x);
-            atomicMin(&s_bb[2], bb.min_y); atomicMax(&s_bb[3], bb.max_y);
+            atomicMin(&s_bb[0], mnx); atomicMax(&s_bb[1], mxx);
+            atomicMin(&s_bb[2], mny); atomicMax(&s_bb[3], mxy);
         }
-        __syncthreads();
+        compute_sync();
         int c0 = 0, c1 = -1, r0 = 0, r1 = -1;
         if (s_bb[0] <= s_bb[1])
         {
@@ -256,129 +471,124 @@ __global__ void __launch_bounds__(DBOT_NT, 1) dbot_particle_kernel(const __grid_
         const bool have_window = (c0 <= c1) && (r0 <= r1);
         const int ww = c1 - c0 + 1;
         float acc = 0.0f;
+        bool copied = false; /* update: the streamed copy of this particle has been awaited */
 
         if (have_window)
         {
-            const int band_rows = max(1, (int)(p.zcap / (uint32_t)ww));
+            const int band_rows = max(1, (int)(p.wcap / (uint32_t)ww));
             for (int rb0 = r0; rb0 <= r1; rb0 += band_rows)
             {
                 const int rb1 = min(rb0 + band_rows - 1, r1);
                 const int npx = (rb1 - rb0 + 1) * ww;
-                __syncthreads(); /* previous band's readers of the z tile are done */
-                for (int q = tid; q < npx; q += DBOT_NT) s_zt[q] = DBOT_Z_EMPTY;
+                compute_sync(); /* previous band's readers of the tile are done */
+                {
+                    uint4* w4 = reinterpret_cast<uint4*>(s_wt);
+                    const int n4 = (npx + 3) >> 2; /* wcap is a multiple of 4 */
+                    for (int q = tid; q < n4; q += DBOT_CT) w4[q] = make_uint4(0u, 0u, 0u, 0u);
+                }
                 if (p.n_chunks == 1)
                 {
-                    __syncthreads();
-                    dbot_raster_triangles(s_tri, p.chunks[0].n_tris, s_X, s_Y, s_x, s_y, s_z, p.K,
-                                          s_zt, rb0, rb1, c0, c1, tid, DBOT_NT);
+                    stage_chunk(0); /* resident after the first particle */
+                    compute_sync();
+                    dbot_raster_chunk(s_tri, p.chunks[0].n_tris, s_v4, s_Y, p.K, s_wt, rb0, rb1, c0,
+                                      c1, warp, lane);
                 }
                 else
                 {
                     for (int c = 0; c < p.n_chunks; ++c)
                     {
-                        stage_chunk(c); /* leading barrier orders z-tile init / previous raster */
+                        stage_chunk(c); /* leading barrier orders tile init / previous raster */
                         const dbot_chunk ch = p.chunks[c];
-                        dbot_bbox dummy = {INT_MAX, INT_MIN, INT_MAX, INT_MIN};
-                        dbot_transform_vertices(s_vert, ch.n_verts, pose + 12 * ch.obj, p.K, s_X,
-                                                s_Y, s_x, s_y, s_z, tid, DBOT_NT, dummy);
-                        __syncthreads();
-                        dbot_raster_triangles(s_tri, ch.n_tris, s_X, s_Y, s_x, s_y, s_z, p.K, s_zt,
-                                              rb0, rb1, c0, c1, tid, DBOT_NT);
+                        int d0 = INT_MAX, d1 = INT_MIN, d2 = INT_MAX, d3 = INT_MIN;
+                        transform_chunk(ch, pose + 12 * ch.obj, d0, d1, d2, d3);
+                        compute_sync();
+                        dbot_raster_chunk(s_tri, ch.n_tris, s_v4, s_Y, p.K, s_wt, rb0, rb1, c0, c1,
+                                          warp, lane);
                     }
                 }
-                __syncthreads();
-                /* ---- per-pixel mixture over the band (coalesced along image rows) ---- */
-                for (int q = tid; q < npx; q += DBOT_NT)
+                compute_sync();
+                if (MODE == DBOT_MODE_UPDATE && !copied)
                 {
-                    const int rr = q / ww;
-                    const int cc = q - rr * ww;
-                    const int r = rb0 + rr, c = c0 + cc;
-                    const uint32_t zb = s_zt[q];
-                    if (MODE == DBOT_MODE_RENDER)
+                    /* the child's slot now holds the propagated parent image everywhere */
+                    mbar_wait(&s_copied, k & 1u);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_consumed);
+                    copied = true;
+                }
+                /* ---- per-pixel mixture over the band: a warp per row, 4 x 32 columns in flight ---- */
+                for (int r = rb0 + warp; r <= rb1; r += DBOT_CW)
+                {
+                    const uint32_t* wrow = s_wt + (r - rb0) * ww;
+                    const size_t grow = (size_t)r * p.pitch + c0;
+                    for (int cb = 0; cb < ww; cb += 128)
                     {
-                        p.depth_out[(size_t)r * p.cols + c] = dbot_u2f(zb);
-                        continue;
+                        uint32_t wb[4];
+                        float4 tab[4];
+                        float o_in[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                        {
+                            const int cc = cb + 32 * j + lane;
+                            wb[j] = (cc < ww) ? wrow[cc] : DBOT_W_EMPTY;
+                        }
+                        if (MODE == DBOT_MODE_RENDER)
+                        {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                            {
+                                const int cc = cb + 32 * j + lane;
+                                if (cc < ww)
+                                    p.depth_out[(size_t)r * p.cols + c0 + cc] = dbot_depth_from_w(wb[j]);
+                            }
+                            continue;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                        {
+                            const int cc = cb + 32 * j + lane;
+                            if (wb[j] != DBOT_W_EMPTY)
+                            {
+                                tab[j] = __ldg(p.tab + grow + cc);
+                                o_in[j] = __ldg(occ_in + grow + cc);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                        {
+                            const int cc = cb + 32 * j + lane;
+                            if (wb[j] != DBOT_W_EMPTY && tab[j].x == tab[j].x)
+                            {
+                                float o_new;
+                                acc = dbot_add(acc, dbot_pixel_term(dbot_rcp(dbot_u2f(wb[j])), tab[j],
+                                                                    o_in[j], p.M, o_new));
+                                if (MODE == DBOT_MODE_UPDATE) __stcs(occ_out + grow + cc, o_new);
+                            }
+                        }
                     }
-                    const size_t gp = (size_t)r * p.pitch + c;
-                    float o_in = 0.0f;
-                    if (MODE == DBOT_MODE_UPDATE) o_in = __ldcs(occ_in + gp);
-                    bool valid = false;
-                    float4 tab;
-                    if (zb != DBOT_Z_EMPTY)
-                    {
-                        tab = __ldg(p.tab + gp);
-                        valid = (tab.x == tab.x);
-                    }
-                    float o_new;
-                    if (valid)
-                    {
-                        if (MODE != DBOT_MODE_UPDATE) o_in = __ldcs(occ_in + gp);
-                        acc += dbot_pixel_term(dbot_u2f(zb), tab, o_in, p.M, o_new);
-                    }
-                    else
-                        o_new = dbot_fmaf(p.M.prop_a, o_in, p.M.prop_b);
-                    if (MODE == DBOT_MODE_UPDATE) __stcs(occ_out + gp, o_new);
                 }
             }
         }
-
-        /* ---- update: stream the rest of the child's occlusion image (propagated parent) ---- */
-        if (MODE == DBOT_MODE_UPDATE)
+        if (MODE == DBOT_MODE_UPDATE && !copied)
         {
-            const int nq = (int)(p.slot_stride >> 2);
-            const float4* in4 = reinterpret_cast<const float4*>(occ_in);
-            float4* out4 = reinterpret_cast<float4*>(occ_out);
-            const float A = p.M.prop_a, B = p.M.prop_b;
-            for (int base = 0; base < nq; base += DBOT_NT * DBOT_STREAM_UNROLL)
-            {
-                float4 v[DBOT_STREAM_UNROLL];
-#pragma unroll
-                for (int k = 0; k < DBOT_STREAM_UNROLL; ++k)
-                {
-                    const int q = base + k * DBOT_NT + tid;
-                    if (q < nq) v[k] = __ldcs(in4 + q);
-                }
-#pragma unroll
-                for (int k = 0; k < DBOT_STREAM_UNROLL; ++k)
-                {
-                    const int q = base + k * DBOT_NT + tid;
-                    if (q >= nq) continue;
-                    const int e = q << 2;
-                    const int r = e / p.pitch;
-                    const int c = e - r * p.pitch;
-                    float4 w;
-                    w.x = dbot_fmaf(A, v[k].x, B);
-                    w.y = dbot_fmaf(A, v[k].y, B);
-                    w.z = dbot_fmaf(A, v[k].z, B);
-                    w.w = dbot_fmaf(A, v[k].w, B);
-                    if (have_window && r >= r0 && r <= r1 && c + 3 >= c0 && c <= c1)
-                    {
-                        /* group touches the window: the window pixels were written above */
-                        float* o = occ_out + e;
-                        if (c < c0 || c > c1) __stcs(o, w.x);
-                        if (c + 1 < c0 || c + 1 > c1) __stcs(o + 1, w.y);
-                        if (c + 2 < c0 || c + 2 > c1) __stcs(o + 2, w.z);
-                        if (c + 3 < c0 || c + 3 > c1) __stcs(o + 3, w.w);
-                    }
-                    else
-                        __stcs(out4 + q, w);
-                }
-            }
+            mbar_wait(&s_copied, k & 1u);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_consumed);
         }
+        ++k;
 
         /* ---- one log-weight per particle: fixed shuffle tree, double across warps ---- */
         if (MODE != DBOT_MODE_RENDER)
         {
             double v = (double)acc;
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(DBOT_FULL, v, off);
             if (lane == 0) s_red[warp] = v;
-            __syncthreads();
+            compute_sync();
             if (tid == 0)
             {
                 double s = 0.0;
 #pragma unroll
-                for (int w = 0; w < DBOT_NT / 32; ++w) s += s_red[w];
+                for (int w = 0; w < DBOT_CW; ++w) s += s_red[w];
                 p.out[i] = s;
                 if (MODE == DBOT_MODE_UPDATE) p.indices[i] = i;
             }
@@ -453,7 +663,9 @@ static uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 /* split every object mesh into chunks of at most DBOT_CHUNK_MAX_VERTS vertices and
  * DBOT_CHUNK_MAX_TRIS triangles with chunk-local uint16 indices (shared vertices are
- * duplicated; a duplicated vertex transforms to bit-identical coordinates). */
+ * duplicated; a duplicated vertex transforms to bit-identical coordinates).  Vertices are
+ * stored as float4 (read once per particle straight from L2), triangle lists as uint16
+ * triples (TMA-staged into shared memory). */
 static int build_chunks(const dbot_b200_config* cfg, std::vector<dbot_chunk>& chunks,
                         std::vector<unsigned char>& blob)
 {
@@ -489,6 +701,7 @@ static int build_chunks(const dbot_b200_config* cfg, std::vector<dbot_chunk>& ch
                         cv.push_back(V[3 * g]);
                         cv.push_back(V[3 * g + 1]);
                         cv.push_back(V[3 * g + 2]);
+                        cv.push_back(0.0f); /* float4 per vertex: one 128-bit load */
                     }
                     ct.push_back(it->second);
                 }
@@ -497,7 +710,7 @@ static int build_chunks(const dbot_b200_config* cfg, std::vector<dbot_chunk>& ch
             dbot_chunk ch;
             memset(&ch, 0, sizeof(ch));
             ch.obj = o;
-            ch.n_verts = (int)cv.size() / 3;
+            ch.n_verts = (int)cv.size() / 4;
             ch.n_tris = (int)ct.size() / 3;
             ch.vert_bytes = round_up((uint32_t)(cv.size() * sizeof(float)), 16);
             ch.tri_bytes = round_up((uint32_t)(ct.size() * sizeof(uint16_t)), 16);
@@ -585,7 +798,7 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     memset(&kp, 0, sizeof(kp));
     kp.rows = cfg->rows;
     kp.cols = cfg->cols;
-    kp.pitch = (int)round_up((uint32_t)cfg->cols, 4);
+    kp.pitch = (int)round_up((uint32_t)cfg->cols, 8); /* 256-bit rows */
     kp.n_obj = cfg->n_objects;
     kp.n_chunks = (int)chunks.size();
     kp.slot_stride = (size_t)kp.rows * kp.pitch;
@@ -607,7 +820,7 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     kp.M.model_sigma = (float)cfg->model_sigma;
     kp.M.sigma_factor = (float)cfg->sigma_factor;
 
-    /* shared-memory carve-up: indices | vertices | X Y x y z | z tile */
+    /* shared-memory carve-up: triangle list | transformed vertices (float4 + Y) | 1/z tile */
     int max_nv = 1, max_nt = 1;
     for (const dbot_chunk& ch : chunks)
     {
@@ -615,20 +828,15 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
         max_nt = std::max(max_nt, ch.n_tris);
     }
     uint32_t off = 0;
-    kp.off_tri = off;  off += round_up((uint32_t)max_nt * 6u, 128);
-    kp.off_vert = off; off += round_up((uint32_t)max_nv * 12u, 128);
-    const uint32_t col = round_up((uint32_t)max_nv * 4u, 128);
-    kp.off_X = off; off += col;
-    kp.off_Y = off; off += col;
-    kp.off_x = off; off += col;
-    kp.off_y = off; off += col;
-    kp.off_z = off; off += col;
-    kp.off_zt = off;
-    const int smem_max = (int)prop.sharedMemPerBlockOptin - 2048; /* static __shared__ + slack */
-    if ((int)off + 4 * kp.cols > smem_max)
-        return fail(-9, "image too wide for the shared-memory z tile (cols=%d)", kp.cols);
+    kp.off_tri = off; off += round_up((uint32_t)max_nt * 6u, 128);
+    kp.off_v4 = off;  off += round_up((uint32_t)max_nv * 16u, 128);
+    kp.off_Y = off;   off += round_up((uint32_t)max_nv * 4u, 128);
+    kp.off_wt = off;
+    const int smem_max = (int)prop.sharedMemPerBlockOptin - 1024; /* static __shared__ + slack */
+    if ((int)off + 4 * (int)round_up((uint32_t)kp.cols, 4) > smem_max)
+        return fail(-9, "image too wide for the shared-memory depth tile (cols=%d)", kp.cols);
     s->smem_bytes = smem_max;
-    kp.zcap = (uint32_t)(smem_max - (int)off) / 4u;
+    kp.wcap = ((uint32_t)(smem_max - (int)off) / 16u) * 4u; /* pixels, multiple of 4 */
     CUDA_TRY(cudaFuncSetAttribute(dbot_particle_kernel<DBOT_MODE_EVAL>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
     CUDA_TRY(cudaFuncSetAttribute(dbot_particle_kernel<DBOT_MODE_UPDATE>,
@@ -793,9 +1001,9 @@ static int launch_particles(dbot_b200_sensor* s, const float* d_poses, int32_t* 
     const int grid = std::min(n, s->grid_max);
     prof_begin(s);
     if (update)
-        dbot_particle_kernel<DBOT_MODE_UPDATE><<<grid, DBOT_NT, s->smem_bytes, s->stream>>>(kp);
+        dbot_particle_kernel<DBOT_MODE_UPDATE><<<grid, DBOT_CT + DBOT_ST, s->smem_bytes, s->stream>>>(kp);
     else
-        dbot_particle_kernel<DBOT_MODE_EVAL><<<grid, DBOT_NT, s->smem_bytes, s->stream>>>(kp);
+        dbot_particle_kernel<DBOT_MODE_EVAL><<<grid, DBOT_CT, s->smem_bytes, s->stream>>>(kp);
     CUDA_TRY(cudaGetLastError());
     prof_end(s, update ? DBOT_B200_KERNEL_UPDATE : DBOT_B200_KERNEL_LOGLIKES);
     if (update)
@@ -886,7 +1094,7 @@ extern "C" int dbot_b200_render(dbot_b200_sensor* s, const float* pose, float* o
         kp.depth_out = s->d_depth;
         kp.err_flag = s->d_err;
         prof_begin(s);
-        dbot_particle_kernel<DBOT_MODE_RENDER><<<1, DBOT_NT, s->smem_bytes, s->stream>>>(kp);
+        dbot_particle_kernel<DBOT_MODE_RENDER><<<1, DBOT_CT, s->smem_bytes, s->stream>>>(kp);
         e = cudaGetLastError();
         prof_end(s, DBOT_B200_KERNEL_RENDER);
     }

@@ -106,7 +106,10 @@ double oracle_propagate(const oracle_sensor* s, double o, double dt) { return pr
  *   - coverage is decided by int64 edge functions on vertices snapped to
  *     1/256 px instead of float span intersections (bit-exact CPU/GPU);
  *   - triangles with a vertex at z' <= 0 are skipped;
- *   - z is clamped to the triangle's own vertex z-range (no-op in exact
+ *   - the z-buffer holds the inverse depth 1/z = n.K^-1 [c,r,1]^T (linear in the
+ *     image plane) and keeps its maximum; the depth 1/(max 1/z) is formed once per
+ *     pixel -- the same pixel wins as with min z, 1/x being monotonic;
+ *   - 1/z is clamped to the triangle's own vertex range (no-op in exact
  *     arithmetic; keeps edge-on triangles from producing wild depths).
  */
 typedef struct
@@ -157,7 +160,7 @@ static inline int32_t floor_div_subpix(int32_t v) { return v >> 8; }
 static inline int32_t imin3(int32_t a, int32_t b, int32_t c) { int32_t m = a < b ? a : b; return m < c ? m : c; }
 static inline int32_t imax3(int32_t a, int32_t b, int32_t c) { int32_t m = a > b ? a : b; return m > c ? m : c; }
 
-static void raster_object(const oracle_sensor* s, int o, const vert_scratch* vs, float* zbuf)
+static void raster_object(const oracle_sensor* s, int o, const vert_scratch* vs, float* wbuf)
 {
     const int rows = s->cfg.rows, cols = s->cfg.cols;
     const int32_t* tri = s->tris[o];
@@ -200,6 +203,8 @@ static void raster_object(const oracle_sensor* s, int o, const vert_scratch* vs,
         float m2 = fmaf(nx, s->k02, fmaf(ny, s->k12, nz));
         float zlo = fminf(az, fminf(vs->z[ib], vs->z[ic]));
         float zhi = fmaxf(az, fmaxf(vs->z[ib], vs->z[ic]));
+        float whi = 1.0f / zlo;
+        float wlo = 1.0f / zhi;
 
         for (int32_t r = rmin; r <= rmax; ++r)
         {
@@ -212,10 +217,9 @@ static void raster_object(const oracle_sensor* s, int o, const vert_scratch* vs,
                 int64_t Eca = (int64_t)(Xa - Xc) * (Py - Yc) - (int64_t)(Ya - Yc) * (Px - Xc);
                 if (sgn * Eab < 0 || sgn * Ebc < 0 || sgn * Eca < 0) continue;
                 float w = fmaf(m0, (float)c, fmaf(m1, (float)r, m2));
-                float z = 1.0f / w;
-                z = fminf(fmaxf(z, zlo), zhi);
-                float* dst = &zbuf[(size_t)r * cols + c];
-                if (z < *dst) *dst = z;
+                w = fminf(fmaxf(w, wlo), whi);
+                float* dst = &wbuf[(size_t)r * cols + c];
+                if (w > *dst) *dst = w;
             }
         }
     }
@@ -224,12 +228,13 @@ static void raster_object(const oracle_sensor* s, int o, const vert_scratch* vs,
 /* full render of one particle: all objects into one z-buffer */
 static void render_particle(const oracle_sensor* s, const float* pose, vert_scratch* vs, float* zbuf)
 {
-    for (int p = 0; p < s->P; ++p) zbuf[p] = INFINITY;
+    for (int p = 0; p < s->P; ++p) zbuf[p] = 0.0f; /* inverse depth 0: nothing hit */
     for (int o = 0; o < s->n_obj; ++o)
     {
         transform_object(s, o, pose + 12 * o, vs);
         raster_object(s, o, vs, zbuf);
     }
+    for (int p = 0; p < s->P; ++p) zbuf[p] = zbuf[p] > 0.0f ? 1.0f / zbuf[p] : INFINITY;
 }
 
 static int alloc_scratch(const oracle_sensor* s, vert_scratch* vs)

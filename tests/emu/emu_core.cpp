@@ -3,8 +3,8 @@
  *
  * Compiles dbot_ros_b200/csrc/particle_core.cuh (the per-particle phase functions of the CUDA
  * kernel) as plain C++ and walks one particle through them sequentially, the way one CTA does
- * between its barriers.  It lets the CPU-only test suite check the kernel's integer raster
- * path, window/band logic and float32 mixture algebra against oracle/ without a GPU.  It is
+ * through them sequentially.  It lets the CPU-only test suite check the kernel's integer raster
+ * arithmetic, window/band logic and float32 mixture algebra against oracle/ without a GPU.  It is
  * built by tests/conftest.py into tests/emu/, is never imported by the package, and is not a
  * fallback: dbot_ros_b200 refuses to run without libdbot_b200.so and a CUDA device.
  */
@@ -79,48 +79,67 @@ double emu_particle(const emu_config* cfg, const float* pose, const float* tab, 
     M.prop_b = prop_b;
 
     /* per-object transformed vertices (the kernel re-stages chunks; here each object is one) */
-    struct tv { std::vector<int> X, Y; std::vector<float> x, y, z; std::vector<uint16_t> tri; };
-    std::vector<tv> objs(cfg->n_objects);
-    dbot_bbox bb = {INT_MAX, INT_MIN, INT_MAX, INT_MIN};
+    std::vector<std::vector<dbot_vertex>> objs(cfg->n_objects);
+    int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
     for (int o = 0; o < cfg->n_objects; ++o)
     {
-        const int nv = cfg->n_vertices[o], nt = cfg->n_triangles[o];
-        tv& t = objs[o];
-        t.X.resize(nv); t.Y.resize(nv); t.x.resize(nv); t.y.resize(nv); t.z.resize(nv);
-        t.tri.resize(3 * nt);
-        for (int i = 0; i < 3 * nt; ++i) t.tri[i] = (uint16_t)cfg->triangles[o][i];
-        dbot_transform_vertices(cfg->vertices[o], nv, pose + 12 * o, K, t.X.data(), t.Y.data(),
-                                t.x.data(), t.y.data(), t.z.data(), 0, 1, bb);
+        const int nv = cfg->n_vertices[o];
+        objs[o].resize(nv);
+        for (int i = 0; i < nv; ++i)
+        {
+            const float* v = cfg->vertices[o] + 3 * i;
+            const dbot_vertex t = dbot_transform_vertex(v[0], v[1], v[2], pose + 12 * o, K);
+            objs[o][i] = t;
+            if (t.X != DBOT_VERT_INVALID)
+            {
+                mnx = t.X < mnx ? t.X : mnx; mxx = t.X > mxx ? t.X : mxx;
+                mny = t.Y < mny ? t.Y : mny; mxy = t.Y > mxy ? t.Y : mxy;
+            }
+        }
     }
     if (depth_out)
         for (int i = 0; i < P; ++i) depth_out[i] = INFINITY;
     int c0 = 0, c1 = -1, r0 = 0, r1 = -1;
-    if (bb.min_x <= bb.max_x)
+    if (mnx <= mxx)
     {
-        c0 = dbot_ceil_subpix(bb.min_x); if (c0 < 0) c0 = 0;
-        c1 = dbot_floor_subpix(bb.max_x); if (c1 > cols - 1) c1 = cols - 1;
-        r0 = dbot_ceil_subpix(bb.min_y); if (r0 < 0) r0 = 0;
-        r1 = dbot_floor_subpix(bb.max_y); if (r1 > rows - 1) r1 = rows - 1;
+        c0 = dbot_ceil_subpix(mnx); if (c0 < 0) c0 = 0;
+        c1 = dbot_floor_subpix(mxx); if (c1 > cols - 1) c1 = cols - 1;
+        r0 = dbot_ceil_subpix(mny); if (r0 < 0) r0 = 0;
+        r1 = dbot_floor_subpix(mxy); if (r1 > rows - 1) r1 = rows - 1;
     }
     const bool have_window = c0 <= c1 && r0 <= r1;
     const int ww = c1 - c0 + 1;
     double acc = 0.0;
-    std::vector<char> in_window(occ_out ? P : 0, 0);
+    /* update: the streaming warps write the propagated parent image everywhere first */
+    if (occ_out)
+        for (int i = 0; i < P; ++i) occ_out[i] = dbot_fmaf(prop_a, occ_in[i], prop_b);
     if (have_window)
     {
         int band_rows = cfg->zcap / ww; if (band_rows < 1) band_rows = 1;
-        std::vector<uint32_t> zt((size_t)band_rows * ww);
+        std::vector<uint32_t> wt((size_t)band_rows * ww);
         for (int rb0 = r0; rb0 <= r1; rb0 += band_rows)
         {
             const int rb1 = rb0 + band_rows - 1 < r1 ? rb0 + band_rows - 1 : r1;
             const int npx = (rb1 - rb0 + 1) * ww;
-            for (int q = 0; q < npx; ++q) zt[q] = DBOT_Z_EMPTY;
+            for (int q = 0; q < npx; ++q) wt[q] = DBOT_W_EMPTY;
             for (int o = 0; o < cfg->n_objects; ++o)
             {
-                tv& t = objs[o];
-                dbot_raster_triangles(t.tri.data(), cfg->n_triangles[o], t.X.data(), t.Y.data(),
-                                      t.x.data(), t.y.data(), t.z.data(), K, zt.data(), rb0, rb1, c0,
-                                      c1, 0, 1);
+                const std::vector<dbot_vertex>& tv = objs[o];
+                for (int t = 0; t < cfg->n_triangles[o]; ++t)
+                {
+                    const int32_t* tri = cfg->triangles[o] + 3 * t;
+                    dbot_tri s;
+                    if (!dbot_setup_triangle(tv[tri[0]], tv[tri[1]], tv[tri[2]], K, rb0, rb1, c0, c1, s))
+                        continue;
+                    for (int r = s.rmin; r <= s.rmax; ++r)
+                        for (int c = s.cmin; c <= s.cmax; ++c)
+                            if (dbot_covers(s, c, r))
+                            {
+                                const uint32_t w = dbot_fragment_w(s, (float)c, (float)r);
+                                uint32_t* dst = &wt[(size_t)(r - rb0) * ww + (c - c0)];
+                                if (w > *dst) *dst = w;
+                            }
+                }
             }
             float facc = 0.f; /* the kernel accumulates float partials per thread */
             int cnt = 0;
@@ -128,32 +147,19 @@ double emu_particle(const emu_config* cfg, const float* pose, const float* tab, 
             {
                 const int rr = q / ww, cc = q - rr * ww;
                 const int gp = (rb0 + rr) * cols + c0 + cc;
-                const uint32_t zb = zt[q];
-                if (depth_out) depth_out[gp] = dbot_u2f(zb);
-                if (!tab) continue;
-                float o_in = occ_in[gp], o_new;
-                bool valid = false;
-                float4 T = {0, 0, 0, 0};
-                if (zb != DBOT_Z_EMPTY)
-                {
-                    T.x = tab[4 * gp]; T.y = tab[4 * gp + 1]; T.z = tab[4 * gp + 2]; T.w = tab[4 * gp + 3];
-                    valid = (T.x == T.x);
-                }
-                if (valid)
-                {
-                    facc += dbot_pixel_term(dbot_u2f(zb), T, o_in, M, o_new);
-                    if (++cnt == 48) { acc += facc; facc = 0.f; cnt = 0; }
-                }
-                else
-                    o_new = dbot_fmaf(prop_a, o_in, prop_b);
-                if (occ_out) { occ_out[gp] = o_new; in_window[gp] = 1; }
+                const uint32_t wb = wt[q];
+                if (depth_out) depth_out[gp] = dbot_depth_from_w(wb);
+                if (!tab || wb == DBOT_W_EMPTY) continue;
+                float4 T = {tab[4 * gp], tab[4 * gp + 1], tab[4 * gp + 2], tab[4 * gp + 3]};
+                if (T.x != T.x) continue;
+                float o_new;
+                facc += dbot_pixel_term(dbot_rcp(dbot_u2f(wb)), T, occ_in[gp], M, o_new);
+                if (++cnt == 48) { acc += facc; facc = 0.f; cnt = 0; }
+                if (occ_out) occ_out[gp] = o_new;
             }
             acc += facc;
         }
     }
-    if (occ_out)
-        for (int i = 0; i < P; ++i)
-            if (!in_window[i]) occ_out[i] = dbot_fmaf(prop_a, occ_in[i], prop_b);
     return acc;
 }
 

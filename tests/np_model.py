@@ -36,7 +36,7 @@ def render(K, rows, cols, vertices, triangles, poses):
     K = np.asarray(K, dtype=np.float64)
     Kf = K.astype(np.float32)
     Kinv = np.linalg.inv(K).astype(np.float32)
-    z = np.full((rows, cols), np.inf, dtype=np.float32)
+    w = np.zeros((rows, cols), dtype=np.float64)
     for V, T, pose in zip(vertices, triangles, poses):
         R = pose[:9].reshape(3, 3).astype(np.float32)
         t = pose[9:].astype(np.float32)
@@ -85,12 +85,12 @@ def render(K, rows, cols, vertices, triangles, poses):
             e2 = sg * ((xa - xc) * (py - yc) - (ya - yc) * (px - xc))
             inside = (e0 >= 0) & (e1 >= 0) & (e2 >= 0)
             wv = m[0] * cc + m[1] * rr + m[2]
-            with np.errstate(divide="ignore", invalid="ignore"):
-                zz = 1.0 / wv
-            zz = np.clip(zz, min(a[2], b[2], c[2]), max(a[2], b[2], c[2])).astype(np.float32)
-            sub = z[rmin:rmax + 1, cmin:cmax + 1]
-            np.minimum(sub, np.where(inside, zz, np.inf), out=sub)
-    return z
+            # inverse depth clamped to the triangle's own vertex range; the largest wins
+            wv = np.clip(wv, 1.0 / max(a[2], b[2], c[2]), 1.0 / min(a[2], b[2], c[2]))
+            sub = w[rmin:rmax + 1, cmin:cmax + 1]
+            np.maximum(sub, np.where(inside, wv, 0.0), out=sub)
+    with np.errstate(divide="ignore"):
+        return np.where(w > 0, 1.0 / w, np.inf).astype(np.float32)
 
 
 def loglike(depth, obs, occ, dt, prm):

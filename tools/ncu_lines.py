@@ -35,15 +35,17 @@ for ln in dis.splitlines():
         line_of[int(m.group(1), 16)] = cur
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-sections, curk = defaultdict(list), None
+sections, curk = [], None
 for r in rows:
     if r and r[0] == "Kernel Name":
-        curk = r[1]
+        curk = (r[1], [])
+        sections.append(curk)
     elif curk:
-        sections[curk].append(r)
-for k, rs in sections.items():
-    if kern.replace("ILi", "<(int)").split("<")[0] not in k and kern not in k:
-        pass
+        curk[1].append(r)
+only = os.environ.get("NCU_LAUNCH")
+for si, (k, rs) in enumerate(sections):
+    if only is not None and si != int(only):
+        continue
     hdr = rs[0]
     ia, ii, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
     stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
