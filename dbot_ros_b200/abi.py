@@ -80,7 +80,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("DBOT_B200_LIB") or LIB_PATH  # env override: profiling variants
     if not os.path.exists(p):
         raise ImportError(
             "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -100,10 +100,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
                  "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
                                             uint64_t* bar)
 {
@@ -131,6 +127,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 __device__ __forceinline__ void compute_sync()
 {
     asm volatile("bar.sync 1, %0;" ::"n"(DBOT_CT) : "memory");
+}
+/* producer/consumer hand-off between the streaming and the compute warps on hardware named
+ * barriers (no polling): the producer side arrives, the consumer side syncs */
+#define DBOT_BAR_COPIED 2
+#define DBOT_BAR_CONSUMED 3
+__device__ __forceinline__ void role_arrive(int id)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(DBOT_CT + DBOT_ST) : "memory");
+}
+__device__ __forceinline__ void role_sync(int id)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(DBOT_CT + DBOT_ST) : "memory");
 }
 __device__ __forceinline__ void ldg256(const float* p, float (&v)[8])
 {
@@ -187,24 +195,60 @@ __global__ void dbot_fill_kernel(float* __restrict__ dst, size_t n, float v)
 
 /* ------------------------------------------------------------------------------------------ */
 /* raster: the triangles of one staged chunk into the inverse-depth tile covering rows
- * [row0,row1] x columns [col0,col1].  A warp takes 32 triangles at a time: every lane sets its
- * triangle up (convergent), then walks its own pixel box with incremental int32 edge functions;
- * triangles whose box is far larger than the batch average (or that need int64 edge functions)
- * are instead walked by the whole warp, 8 x 4 pixels per step.                                 */
+ * [row0,row1] x columns [col0,col1].
+ *
+ * A warp takes 32 triangles at a time (batches handed out by a shared-memory counter); every
+ * lane sets its own triangle up (convergent).  The pixel boxes of the 32 triangles are cut into
+ * blocks of 8 columns x 2 rows and the blocks are dealt out evenly over the lanes (prefix sum
+ * over the block counts, binary search, owner's parameters by shuffle), so every lane always
+ * has a block to work on however unequal the triangles are.  A block is processed without a
+ * single branch: 16 x (three incremental int32 edge functions, sign test, one fma for the
+ * inverse depth, predicated shared-memory read + atomicMax on the bits of the positive float).
+ * Triangles that need int64 edge functions or whose box dwarfs the batch are instead walked by
+ * the whole warp, 8 x 4 pixels per step.                                                      */
 __device__ __forceinline__ void dbot_zmax(uint32_t* p, uint32_t v)
 {
     if (v > *p) atomicMax(p, v); /* plain read first: fragments that lose the test cost no atomic */
+}
+/* One pixel of a block, fully predicated (no branch): covered = all three edge functions >= 0
+ * and the pixel's bit set in the block's validity mask; a covered fragment reads the tile and
+ * only issues the shared-memory max when it wins. */
+template <int BIT>
+__device__ __forceinline__ void dbot_fragment_pred(uint32_t tile_addr, uint32_t bits, int y0, int y1,
+                                                   int y2, uint32_t vmask)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .u32 cur, t;\n"
+        "or.b32 t, %2, %3;\n"
+        "or.b32 t, t, %4;\n"
+        "setp.ge.s32 p, t, 0;\n"
+        "and.b32 t, %5, %6;\n"
+        "setp.ne.and.u32 p, t, 0, p;\n"
+        "mov.u32 cur, 0xffffffff;\n"
+        "@p ld.shared.u32 cur, [%0];\n"
+        "setp.gt.u32 q, %1, cur;\n"
+        "@q red.shared.max.u32 [%0], %1;\n"
+        "}" ::"r"(tile_addr),
+        "r"(bits), "r"(y0), "r"(y1), "r"(y2), "r"(vmask), "n"(1u << BIT)
+        : "memory");
 }
 
 __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s_tri, int ntri,
                                                   const float4* __restrict__ s_v4,
                                                   const int* __restrict__ s_Y, const dbot_camera& K,
-                                                  uint32_t* s_wt, int row0, int row1, int col0,
-                                                  int col1, int warp, int lane)
+                                                  uint32_t* s_wt, int* s_batch, int row0, int row1,
+                                                  int col0, int col1, int lane)
 {
     const int ww = col1 - col0 + 1;
-    for (int base = warp * 32; base < ntri; base += DBOT_CW * 32)
+    const uint32_t tile_s = smem_u32(s_wt);
+    for (;;)
     {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(s_batch, 32);
+        base = __shfl_sync(DBOT_FULL, base, 0);
+        if (base >= ntri) break;
         const int t = base + lane;
         dbot_tri s;
         bool ok = false;
@@ -218,50 +262,103 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
             c.x = pc.x; c.y = pc.y; c.z = pc.z; c.X = __float_as_int(pc.w); c.Y = s_Y[ic];
             ok = dbot_setup_triangle(a, b, c, K, row0, row1, col0, col1, s);
         }
-        const int area = ok ? (s.cmax - s.cmin + 1) * (s.rmax - s.rmin + 1) : 0;
-        int tot = area;
+        __syncwarp();
+        const int bw = ok ? (s.cmax - s.cmin + 8) >> 3 : 0; /* blocks of 8 columns */
+        const int bh = ok ? (s.rmax - s.rmin + 2) >> 1 : 0; /* blocks of 2 rows */
+        int tot = bw * bh;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(DBOT_FULL, tot, off);
-        const int thresh = max(64, tot >> 3); /* 4 x the batch mean */
-        const bool big = ok && (area > thresh || !s.small);
+        const bool big = ok && (!s.small || bw * bh > max(16, tot >> 3)); /* > 4 x the batch mean */
+        const bool mine = ok && !big;
+        const int nb = mine ? bw * bh : 0;
 
-        if (ok && !big)
+        /* edge functions at (cmin, rmin), oriented so that inside means all three >= 0 */
+        int e0c = 0, e1c = 0, e2c = 0, e0r = 0, e1r = 0, e2r = 0, A0 = -1, A1 = -1, A2 = -1;
+        if (mine)
         {
-            int e0c = -(s.Yb - s.Ya) * DBOT_SUBPIX, e0r = (s.Xb - s.Xa) * DBOT_SUBPIX;
-            int e1c = -(s.Yc - s.Yb) * DBOT_SUBPIX, e1r = (s.Xc - s.Xb) * DBOT_SUBPIX;
-            int e2c = -(s.Ya - s.Yc) * DBOT_SUBPIX, e2r = (s.Xa - s.Xc) * DBOT_SUBPIX;
+            e0c = -(s.Yb - s.Ya) * DBOT_SUBPIX; e0r = (s.Xb - s.Xa) * DBOT_SUBPIX;
+            e1c = -(s.Yc - s.Yb) * DBOT_SUBPIX; e1r = (s.Xc - s.Xb) * DBOT_SUBPIX;
+            e2c = -(s.Ya - s.Yc) * DBOT_SUBPIX; e2r = (s.Xa - s.Xc) * DBOT_SUBPIX;
             const int px0 = s.cmin * DBOT_SUBPIX, py0 = s.rmin * DBOT_SUBPIX;
-            int e0 = (s.Xb - s.Xa) * (py0 - s.Ya) - (s.Yb - s.Ya) * (px0 - s.Xa);
-            int e1 = (s.Xc - s.Xb) * (py0 - s.Yb) - (s.Yc - s.Yb) * (px0 - s.Xb);
-            int e2 = (s.Xa - s.Xc) * (py0 - s.Yc) - (s.Ya - s.Yc) * (px0 - s.Xc);
+            A0 = (s.Xb - s.Xa) * (py0 - s.Ya) - (s.Yb - s.Ya) * (px0 - s.Xa);
+            A1 = (s.Xc - s.Xb) * (py0 - s.Yb) - (s.Yc - s.Yb) * (px0 - s.Xb);
+            A2 = (s.Xa - s.Xc) * (py0 - s.Yc) - (s.Ya - s.Yc) * (px0 - s.Xc);
             if (s.flip)
             {
-                e0 = -e0; e1 = -e1; e2 = -e2;
+                A0 = -A0; A1 = -A1; A2 = -A2;
                 e0c = -e0c; e1c = -e1c; e2c = -e2c;
                 e0r = -e0r; e1r = -e1r; e2r = -e2r;
             }
-            const float fc0 = (float)s.cmin;
-            float fr = (float)s.rmin;
-            uint32_t* wrow = s_wt + (s.rmin - row0) * ww - col0;
-            for (int r = s.rmin; r <= s.rmax; ++r)
+        }
+        const int cspan = s.cmin | (s.cmax << 16), rspan = s.rmin | (s.rmax << 16);
+        /* inclusive prefix sum of the block counts */
+        int P = nb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const int v = __shfl_up_sync(DBOT_FULL, P, d);
+            if (lane >= d) P += v;
+        }
+        const int H = __shfl_sync(DBOT_FULL, P, 31);
+        const int Pex = P - nb;
+
+        for (int qb = 0; qb < H; qb += 32)
+        {
+            const int q = qb + lane;
+            /* owner of block q: the first lane whose inclusive prefix exceeds q */
+            int j = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
             {
-                int a0 = e0, a1 = e1, a2 = e2;
-                float fc = fc0;
-                const float wr = dbot_fmaf(s.m1, fr, s.m2);
-                for (int c = s.cmin; c <= s.cmax; ++c)
-                {
-                    if ((a0 | a1 | a2) >= 0)
-                    {
-                        const float w = dbot_fmaf(s.m0, fc, wr);
-                        dbot_zmax(wrow + c, dbot_f2u(fminf(fmaxf(w, s.wlo), s.whi)));
-                    }
-                    a0 += e0c; a1 += e1c; a2 += e2c;
-                    fc = dbot_add(fc, 1.0f);
-                }
-                e0 += e0r; e1 += e1r; e2 += e2r;
-                fr = dbot_add(fr, 1.0f);
-                wrow += ww;
+                const int v = __shfl_sync(DBOT_FULL, P, (j + step - 1) & 31);
+                if (v <= q) j += step;
             }
+            j &= 31;
+            const int idx = q - __shfl_sync(DBOT_FULL, Pex, j);
+            const int o_cspan = __shfl_sync(DBOT_FULL, cspan, j), o_rspan = __shfl_sync(DBOT_FULL, rspan, j);
+            const int o_e0c = __shfl_sync(DBOT_FULL, e0c, j), o_e1c = __shfl_sync(DBOT_FULL, e1c, j),
+                      o_e2c = __shfl_sync(DBOT_FULL, e2c, j);
+            const int o_e0r = __shfl_sync(DBOT_FULL, e0r, j), o_e1r = __shfl_sync(DBOT_FULL, e1r, j),
+                      o_e2r = __shfl_sync(DBOT_FULL, e2r, j);
+            const int o_A0 = __shfl_sync(DBOT_FULL, A0, j), o_A1 = __shfl_sync(DBOT_FULL, A1, j),
+                      o_A2 = __shfl_sync(DBOT_FULL, A2, j);
+            const float o_m0 = __shfl_sync(DBOT_FULL, s.m0, j), o_m1 = __shfl_sync(DBOT_FULL, s.m1, j),
+                        o_m2 = __shfl_sync(DBOT_FULL, s.m2, j);
+            const float o_wlo = __shfl_sync(DBOT_FULL, s.wlo, j), o_whi = __shfl_sync(DBOT_FULL, s.whi, j);
+            const int o_cmin = o_cspan & 0xffff, o_cmax = o_cspan >> 16;
+            const int o_rmin = o_rspan & 0xffff, o_rmax = o_rspan >> 16;
+            const int o_bw = (o_cmax - o_cmin + 8) >> 3;
+            /* idx -> (row pair, column block); exact for these small integers */
+            const int pr = (o_bw == 1) ? idx : __float2int_rz(__fdividef((float)idx + 0.5f, (float)o_bw));
+            const int bx = idx - pr * o_bw;
+            const int cx0 = o_cmin + 8 * bx, ry0 = o_rmin + 2 * pr;
+            const int nc = (q < H) ? min(8, o_cmax - cx0 + 1) : 0;
+            const uint32_t colm = (1u << nc) - 1u;
+            const uint32_t vmask = colm | ((ry0 + 1 <= o_rmax) ? (colm << 8) : 0u);
+            int x0 = o_A0 + (8 * bx) * o_e0c + (2 * pr) * o_e0r;
+            int x1 = o_A1 + (8 * bx) * o_e1c + (2 * pr) * o_e1r;
+            int x2 = o_A2 + (8 * bx) * o_e2c + (2 * pr) * o_e2r;
+            const float fc0 = (float)cx0, fr0 = (float)ry0;
+            const uint32_t tp = tile_s + 4u * (uint32_t)((ry0 - row0) * ww + (cx0 - col0));
+#define DBOT_PIXEL(RR, CC)                                                                         \
+    {                                                                                              \
+        const float w = dbot_fmaf(o_m0, dbot_add(fc0, (float)(CC)), wr);                           \
+        dbot_fragment_pred<8 * (RR) + (CC)>(trow + 4u * (CC), dbot_f2u(fminf(fmaxf(w, o_wlo), o_whi)), \
+                                            x0 + (CC) * o_e0c, x1 + (CC) * o_e1c, x2 + (CC) * o_e2c, \
+                                            vmask);                                                \
+    }
+#define DBOT_ROW(RR)                                                                               \
+    {                                                                                              \
+        const float wr = dbot_fmaf(o_m1, dbot_add(fr0, (float)(RR)), o_m2);                        \
+        const uint32_t trow = tp + 4u * (uint32_t)((RR) * ww);                                     \
+        DBOT_PIXEL(RR, 0) DBOT_PIXEL(RR, 1) DBOT_PIXEL(RR, 2) DBOT_PIXEL(RR, 3)                    \
+        DBOT_PIXEL(RR, 4) DBOT_PIXEL(RR, 5) DBOT_PIXEL(RR, 6) DBOT_PIXEL(RR, 7)                    \
+        x0 += o_e0r; x1 += o_e1r; x2 += o_e2r;                                                     \
+    }
+            DBOT_ROW(0)
+            DBOT_ROW(1)
+#undef DBOT_ROW
+#undef DBOT_PIXEL
         }
         __syncwarp();
 
@@ -303,16 +400,15 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
  * Warp roles: warps [0, DBOT_CW) compute; in update launches warps [DBOT_CW, DBOT_CW+DBOT_SW)
  * stream the parent's propagated occlusion image into the child's slot while the compute warps
  * transform and rasterise the same particle; the compute warps then overwrite the covered
- * pixels with the posterior.  Hand-off through two mbarriers (image copied / copy consumed). */
+ * pixels with the posterior.  Hand-off through two named barriers (copied / consumed). */
 template <int MODE>
 __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST : 0), 1)
     dbot_particle_kernel(const __grid_constant__ dbot_kparams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_bar;      /* TMA mesh staging */
-    __shared__ __align__(8) uint64_t s_copied;   /* streaming warps -> compute warps */
-    __shared__ __align__(8) uint64_t s_consumed; /* compute warps -> streaming warps */
     __shared__ int s_bb[4];
+    __shared__ int s_batch;                      /* next triangle batch of the current raster pass */
     __shared__ double s_red[DBOT_CW];
 
     const int tid = threadIdx.x;
@@ -320,8 +416,6 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
     if (tid == 0)
     {
         mbar_init(&s_bar, 1);
-        mbar_init(&s_copied, DBOT_ST);
-        mbar_init(&s_consumed, DBOT_CW);
         mbar_fence_init();
     }
     __syncthreads();
@@ -332,15 +426,15 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
         const int sl = tid - DBOT_CT;
         const int n8 = (int)(p.slot_stride >> 3);
         const float A = p.M.prop_a, B = p.M.prop_b;
-        uint32_t k = 0;
         for (int i = blockIdx.x; i < p.n; i += gridDim.x)
         {
             const int slot = p.indices[i];
             if (slot < 0 || slot >= p.n_slots) continue;
-            /* at most one particle ahead of the compute warps */
-            if (k > 0) mbar_wait(&s_consumed, (k - 1) & 1u);
             const float* in = p.occ_in + (size_t)slot * p.slot_stride;
             float* out = p.occ_out + (size_t)i * p.slot_stride;
+#ifdef DBOT_DBG_NO_STREAM
+            if (p.n == 0x7654321)
+#endif
             for (int base = sl; base < n8; base += DBOT_ST * DBOT_STREAM_UNROLL)
             {
                 float v[DBOT_STREAM_UNROLL][8];
@@ -362,8 +456,9 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                     }
                 }
             }
-            mbar_arrive(&s_copied);
-            ++k;
+            role_arrive(DBOT_BAR_COPIED);
+            /* at most one particle ahead: wait until the compute warps have taken this copy */
+            role_sync(DBOT_BAR_CONSUMED);
         }
         return;
     }
@@ -375,7 +470,6 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
     uint32_t* s_wt = (uint32_t*)(smem + p.off_wt);
     uint32_t parity = 0;
     int staged = -1;
-    uint32_t k = 0;
 
     /* TMA-stage the triangle list of one mesh chunk: one thread arms the mbarrier with the
      * byte count and issues the bulk copy; every compute thread waits on the barrier phase. */
@@ -489,9 +583,10 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                 if (p.n_chunks == 1)
                 {
                     stage_chunk(0); /* resident after the first particle */
+                    if (tid == 0) s_batch = 0;
                     compute_sync();
-                    dbot_raster_chunk(s_tri, p.chunks[0].n_tris, s_v4, s_Y, p.K, s_wt, rb0, rb1, c0,
-                                      c1, warp, lane);
+                    dbot_raster_chunk(s_tri, p.chunks[0].n_tris, s_v4, s_Y, p.K, s_wt, &s_batch, rb0,
+                                      rb1, c0, c1, lane);
                 }
                 else
                 {
@@ -501,21 +596,24 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                         const dbot_chunk ch = p.chunks[c];
                         int d0 = INT_MAX, d1 = INT_MIN, d2 = INT_MAX, d3 = INT_MIN;
                         transform_chunk(ch, pose + 12 * ch.obj, d0, d1, d2, d3);
+                        if (tid == 0) s_batch = 0;
                         compute_sync();
-                        dbot_raster_chunk(s_tri, ch.n_tris, s_v4, s_Y, p.K, s_wt, rb0, rb1, c0, c1,
-                                          warp, lane);
+                        dbot_raster_chunk(s_tri, ch.n_tris, s_v4, s_Y, p.K, s_wt, &s_batch, rb0, rb1,
+                                          c0, c1, lane);
                     }
                 }
                 compute_sync();
                 if (MODE == DBOT_MODE_UPDATE && !copied)
                 {
                     /* the child's slot now holds the propagated parent image everywhere */
-                    mbar_wait(&s_copied, k & 1u);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_consumed);
+                    role_sync(DBOT_BAR_COPIED);
+                    role_arrive(DBOT_BAR_CONSUMED);
                     copied = true;
                 }
                 /* ---- per-pixel mixture over the band: a warp per row, 4 x 32 columns in flight ---- */
+#ifdef DBOT_DBG_NO_PIXELS
+                if (p.n == 0x7654321)
+#endif
                 for (int r = rb0 + warp; r <= rb1; r += DBOT_CW)
                 {
                     const uint32_t* wrow = s_wt + (r - rb0) * ww;
@@ -570,11 +668,9 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
         }
         if (MODE == DBOT_MODE_UPDATE && !copied)
         {
-            mbar_wait(&s_copied, k & 1u);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_consumed);
+            role_sync(DBOT_BAR_COPIED);
+            role_arrive(DBOT_BAR_CONSUMED);
         }
-        ++k;
 
         /* ---- one log-weight per particle: fixed shuffle tree, double across warps ---- */
         if (MODE != DBOT_MODE_RENDER)
