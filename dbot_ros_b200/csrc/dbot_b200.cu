@@ -37,10 +37,20 @@
 #define DBOT_CT (DBOT_CW * 32)     /* compute threads */
 #define DBOT_SW 4                  /* streaming warps per CTA (update launches only) */
 #define DBOT_ST (DBOT_SW * 32)
-#define DBOT_STREAM_UNROLL 8       /* 256-bit loads in flight per streaming thread */
+#define DBOT_STREAM_UNROLL 4       /* 256-bit loads in flight per streaming thread */
+/* update launches start every thread with 96 registers (640 threads); the streaming warp group
+ * hands most of its share to the four compute warp groups (setmaxnreg) */
+#ifndef DBOT_PREFETCH_AHEAD
+#define DBOT_PREFETCH_AHEAD 8      /* chunks of DBOT_ST x DBOT_STREAM_UNROLL x 32 B (16 KB) */
+#endif
+#define DBOT_STREAM_REGS 56
+#define DBOT_COMPUTE_REGS 104
 #define DBOT_CHUNK_MAX_VERTS 3072
 #define DBOT_CHUNK_MAX_TRIS 6144
 #define DBOT_FULL 0xffffffffu
+#ifndef DBOT_UNIT_PX
+#define DBOT_UNIT_PX 4             /* pixels per lane and unit of the mixture pass */
+#endif
 
 enum
 {
@@ -199,47 +209,55 @@ __global__ void dbot_fill_kernel(float* __restrict__ dst, size_t n, float v)
  *
  * A warp takes 32 triangles at a time (batches handed out by a shared-memory counter); every
  * lane sets its own triangle up (convergent).  The pixel boxes of the 32 triangles are cut into
- * blocks of 8 columns x 2 rows and the blocks are dealt out evenly over the lanes (prefix sum
- * over the block counts, binary search, owner's parameters by shuffle), so every lane always
- * has a block to work on however unequal the triangles are.  A block is processed without a
- * single branch: 16 x (three incremental int32 edge functions, sign test, one fma for the
- * inverse depth, predicated shared-memory read + atomicMax on the bits of the positive float).
- * Triangles that need int64 edge functions or whose box dwarfs the batch are instead walked by
- * the whole warp, 8 x 4 pixels per step.                                                      */
+ * blocks of 8 columns x 4 rows and the blocks are dealt out evenly over the lanes (prefix sum
+ * over the block counts, owner table in shared memory, owner's parameters by shuffle), so every
+ * lane always has a block to work on however unequal the triangles are.  A block is processed
+ * row by row without branches on coverage: 8 x (three int32 edge functions, sign test, one fma
+ * for the inverse depth, predicated read of the tile), then 8 x (compare, shared-memory max on
+ * the bits of the positive float for the fragments that win).
+ * Pixels of a block outside the triangle's own box fail the edge test by themselves, so no
+ * box mask is needed -- unless the box was cut by the raster window; those triangles, the ones
+ * that need int64 edge functions and the ones whose box dwarfs the batch are instead walked by
+ * the whole warp, 8 x 4 pixels per step with explicit bounds.                                  */
+#define DBOT_OWNER_CAP 512 /* blocks per batch: 32 lanes x at most 16 blocks each */
+
 __device__ __forceinline__ void dbot_zmax(uint32_t* p, uint32_t v)
 {
     if (v > *p) atomicMax(p, v); /* plain read first: fragments that lose the test cost no atomic */
 }
-/* One pixel of a block, fully predicated (no branch): covered = all three edge functions >= 0
- * and the pixel's bit set in the block's validity mask; a covered fragment reads the tile and
- * only issues the shared-memory max when it wins. */
-template <int BIT>
-__device__ __forceinline__ void dbot_fragment_pred(uint32_t tile_addr, uint32_t bits, int y0, int y1,
-                                                   int y2, uint32_t vmask)
+/* predicated tile read: the current inverse depth where the pixel is covered, else "infinitely
+ * near" so that the fragment loses */
+__device__ __forceinline__ uint32_t dbot_tile_read_if(uint32_t tile_addr, int edge_or)
+{
+    uint32_t cur = 0xffffffffu;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ge.s32 p, %1, 0;\n"
+        "@p ld.shared.u32 %0, [%2];\n"
+        "}"
+        : "+r"(cur)
+        : "r"(edge_or), "r"(tile_addr)
+        : "memory");
+    return cur;
+}
+__device__ __forceinline__ void dbot_tile_max_if(uint32_t tile_addr, uint32_t bits, uint32_t cur)
 {
     asm volatile(
         "{\n"
-        ".reg .pred p, q;\n"
-        ".reg .u32 cur, t;\n"
-        "or.b32 t, %2, %3;\n"
-        "or.b32 t, t, %4;\n"
-        "setp.ge.s32 p, t, 0;\n"
-        "and.b32 t, %5, %6;\n"
-        "setp.ne.and.u32 p, t, 0, p;\n"
-        "mov.u32 cur, 0xffffffff;\n"
-        "@p ld.shared.u32 cur, [%0];\n"
-        "setp.gt.u32 q, %1, cur;\n"
+        ".reg .pred q;\n"
+        "setp.gt.u32 q, %1, %2;\n"
         "@q red.shared.max.u32 [%0], %1;\n"
         "}" ::"r"(tile_addr),
-        "r"(bits), "r"(y0), "r"(y1), "r"(y2), "r"(vmask), "n"(1u << BIT)
+        "r"(bits), "r"(cur)
         : "memory");
 }
 
 __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s_tri, int ntri,
                                                   const float4* __restrict__ s_v4,
                                                   const int* __restrict__ s_Y, const dbot_camera& K,
-                                                  uint32_t* s_wt, int* s_batch, int row0, int row1,
-                                                  int col0, int col1, int lane)
+                                                  uint32_t* s_wt, unsigned char* s_owner, int* s_batch,
+                                                  int row0, int row1, int col0, int col1, int lane)
 {
     const int ww = col1 - col0 + 1;
     const uint32_t tile_s = smem_u32(s_wt);
@@ -264,11 +282,12 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
         }
         __syncwarp();
         const int bw = ok ? (s.cmax - s.cmin + 8) >> 3 : 0; /* blocks of 8 columns */
-        const int bh = ok ? (s.rmax - s.rmin + 2) >> 1 : 0; /* blocks of 2 rows */
+        const int bh = ok ? (s.rmax - s.rmin + 4) >> 2 : 0; /* blocks of 4 rows */
         int tot = bw * bh;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(DBOT_FULL, tot, off);
-        const bool big = ok && (!s.small || bw * bh > max(16, tot >> 3)); /* > 4 x the batch mean */
+        /* whole-warp walk: int64 edge functions, window-cut boxes, > 4 x the batch mean */
+        const bool big = ok && (!s.small || s.clipped || bw * bh > min(16, max(8, tot >> 3)));
         const bool mine = ok && !big;
         const int nb = mine ? bw * bh : 0;
 
@@ -290,8 +309,9 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
                 e0r = -e0r; e1r = -e1r; e2r = -e2r;
             }
         }
-        const int cspan = s.cmin | (s.cmax << 16), rspan = s.rmin | (s.rmax << 16);
-        /* inclusive prefix sum of the block counts */
+        /* origin of the box and its width in blocks, packed: cmin | rmin << 12 | bw << 24 */
+        const int origin = mine ? (s.cmin | (s.rmin << 12) | (bw << 24)) : 0;
+        /* inclusive prefix sum of the block counts, owner table */
         int P = nb;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1)
@@ -299,66 +319,69 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
             const int v = __shfl_up_sync(DBOT_FULL, P, d);
             if (lane >= d) P += v;
         }
+#ifdef DBOT_DBG_NO_SWEEP
+        const int H = (A0 == 0x7654321) ? 1 : 0;
+#else
         const int H = __shfl_sync(DBOT_FULL, P, 31);
+#endif
         const int Pex = P - nb;
+        for (int k = 0; k < nb; ++k) s_owner[Pex + k] = (unsigned char)lane;
+        __syncwarp();
 
         for (int qb = 0; qb < H; qb += 32)
         {
             const int q = qb + lane;
-            /* owner of block q: the first lane whose inclusive prefix exceeds q */
-            int j = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1)
-            {
-                const int v = __shfl_sync(DBOT_FULL, P, (j + step - 1) & 31);
-                if (v <= q) j += step;
-            }
-            j &= 31;
+            const bool active = q < H;
+            const int j = active ? s_owner[q] : 0;
             const int idx = q - __shfl_sync(DBOT_FULL, Pex, j);
-            const int o_cspan = __shfl_sync(DBOT_FULL, cspan, j), o_rspan = __shfl_sync(DBOT_FULL, rspan, j);
-            const int o_e0c = __shfl_sync(DBOT_FULL, e0c, j), o_e1c = __shfl_sync(DBOT_FULL, e1c, j),
-                      o_e2c = __shfl_sync(DBOT_FULL, e2c, j);
-            const int o_e0r = __shfl_sync(DBOT_FULL, e0r, j), o_e1r = __shfl_sync(DBOT_FULL, e1r, j),
-                      o_e2r = __shfl_sync(DBOT_FULL, e2r, j);
+            const int o_origin = __shfl_sync(DBOT_FULL, origin, j);
+            int o_e0c = __shfl_sync(DBOT_FULL, e0c, j), o_e1c = __shfl_sync(DBOT_FULL, e1c, j),
+                o_e2c = __shfl_sync(DBOT_FULL, e2c, j);
+            int o_e0r = __shfl_sync(DBOT_FULL, e0r, j);
+            const int o_e1r = __shfl_sync(DBOT_FULL, e1r, j), o_e2r = __shfl_sync(DBOT_FULL, e2r, j);
             const int o_A0 = __shfl_sync(DBOT_FULL, A0, j), o_A1 = __shfl_sync(DBOT_FULL, A1, j),
                       o_A2 = __shfl_sync(DBOT_FULL, A2, j);
             const float o_m0 = __shfl_sync(DBOT_FULL, s.m0, j), o_m1 = __shfl_sync(DBOT_FULL, s.m1, j),
                         o_m2 = __shfl_sync(DBOT_FULL, s.m2, j);
             const float o_wlo = __shfl_sync(DBOT_FULL, s.wlo, j), o_whi = __shfl_sync(DBOT_FULL, s.whi, j);
-            const int o_cmin = o_cspan & 0xffff, o_cmax = o_cspan >> 16;
-            const int o_rmin = o_rspan & 0xffff, o_rmax = o_rspan >> 16;
-            const int o_bw = (o_cmax - o_cmin + 8) >> 3;
-            /* idx -> (row pair, column block); exact for these small integers */
+            const int o_bw = o_origin >> 24;
+            /* idx -> (row block, column block); exact for these small integers */
             const int pr = (o_bw == 1) ? idx : __float2int_rz(__fdividef((float)idx + 0.5f, (float)o_bw));
             const int bx = idx - pr * o_bw;
-            const int cx0 = o_cmin + 8 * bx, ry0 = o_rmin + 2 * pr;
-            const int nc = (q < H) ? min(8, o_cmax - cx0 + 1) : 0;
-            const uint32_t colm = (1u << nc) - 1u;
-            const uint32_t vmask = colm | ((ry0 + 1 <= o_rmax) ? (colm << 8) : 0u);
-            int x0 = o_A0 + (8 * bx) * o_e0c + (2 * pr) * o_e0r;
-            int x1 = o_A1 + (8 * bx) * o_e1c + (2 * pr) * o_e1r;
-            int x2 = o_A2 + (8 * bx) * o_e2c + (2 * pr) * o_e2r;
-            const float fc0 = (float)cx0, fr0 = (float)ry0;
-            const uint32_t tp = tile_s + 4u * (uint32_t)((ry0 - row0) * ww + (cx0 - col0));
-#define DBOT_PIXEL(RR, CC)                                                                         \
-    {                                                                                              \
-        const float w = dbot_fmaf(o_m0, dbot_add(fc0, (float)(CC)), wr);                           \
-        dbot_fragment_pred<8 * (RR) + (CC)>(trow + 4u * (CC), dbot_f2u(fminf(fmaxf(w, o_wlo), o_whi)), \
-                                            x0 + (CC) * o_e0c, x1 + (CC) * o_e1c, x2 + (CC) * o_e2c, \
-                                            vmask);                                                \
-    }
-#define DBOT_ROW(RR)                                                                               \
-    {                                                                                              \
-        const float wr = dbot_fmaf(o_m1, dbot_add(fr0, (float)(RR)), o_m2);                        \
-        const uint32_t trow = tp + 4u * (uint32_t)((RR) * ww);                                     \
-        DBOT_PIXEL(RR, 0) DBOT_PIXEL(RR, 1) DBOT_PIXEL(RR, 2) DBOT_PIXEL(RR, 3)                    \
-        DBOT_PIXEL(RR, 4) DBOT_PIXEL(RR, 5) DBOT_PIXEL(RR, 6) DBOT_PIXEL(RR, 7)                    \
-        x0 += o_e0r; x1 += o_e1r; x2 += o_e2r;                                                     \
-    }
-            DBOT_ROW(0)
-            DBOT_ROW(1)
-#undef DBOT_ROW
-#undef DBOT_PIXEL
+            const int cx0 = (o_origin & 0xfff) + 8 * bx, ry0 = ((o_origin >> 12) & 0xfff) + 4 * pr;
+            int x0 = o_A0 + (8 * bx) * o_e0c + (4 * pr) * o_e0r;
+            int x1 = o_A1 + (8 * bx) * o_e1c + (4 * pr) * o_e1r;
+            int x2 = o_A2 + (8 * bx) * o_e2c + (4 * pr) * o_e2r;
+            if (!active) /* nothing to do in the last, partial round: every test fails */
+            {
+                x0 = -1;
+                o_e0c = 0;
+                o_e0r = 0;
+            }
+            const float fc0 = (float)cx0;
+            float fr = (float)ry0;
+            uint32_t trow = tile_s + 4u * (uint32_t)((ry0 - row0) * ww + (cx0 - col0));
+            float fc[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) fc[cc] = dbot_add(fc0, (float)cc);
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr)
+            {
+                const float wr = dbot_fmaf(o_m1, fr, o_m2);
+                uint32_t bits[8], cur[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                {
+                    const int eor = (x0 + cc * o_e0c) | (x1 + cc * o_e1c) | (x2 + cc * o_e2c);
+                    bits[cc] = dbot_f2u(fminf(fmaxf(dbot_fmaf(o_m0, fc[cc], wr), o_wlo), o_whi));
+                    cur[cc] = dbot_tile_read_if(trow + 4u * cc, eor);
+                }
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) dbot_tile_max_if(trow + 4u * cc, bits[cc], cur[cc]);
+                x0 += o_e0r; x1 += o_e1r; x2 += o_e2r;
+                fr = dbot_add(fr, 1.0f);
+                trow += 4u * (uint32_t)ww;
+            }
         }
         __syncwarp();
 
@@ -375,6 +398,7 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
             q.rmin = __shfl_sync(DBOT_FULL, s.rmin, j); q.rmax = __shfl_sync(DBOT_FULL, s.rmax, j);
             q.flip = __shfl_sync(DBOT_FULL, s.flip, j);
             q.small = 0;
+            q.clipped = 0;
             q.m0 = __shfl_sync(DBOT_FULL, s.m0, j); q.m1 = __shfl_sync(DBOT_FULL, s.m1, j);
             q.m2 = __shfl_sync(DBOT_FULL, s.m2, j);
             q.wlo = __shfl_sync(DBOT_FULL, s.wlo, j); q.whi = __shfl_sync(DBOT_FULL, s.whi, j);
@@ -409,6 +433,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
     __shared__ __align__(8) uint64_t s_bar;      /* TMA mesh staging */
     __shared__ int s_bb[4];
     __shared__ int s_batch;                      /* next triangle batch of the current raster pass */
+    __shared__ unsigned char s_owner_all[DBOT_CW][DBOT_OWNER_CAP]; /* block -> owning lane, per warp */
     __shared__ double s_red[DBOT_CW];
 
     const int tid = threadIdx.x;
@@ -423,20 +448,62 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
     /* ================= streaming warps (update launches only) ================= */
     if (MODE == DBOT_MODE_UPDATE && warp >= DBOT_CW)
     {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DBOT_STREAM_REGS));
         const int sl = tid - DBOT_CT;
         const int n8 = (int)(p.slot_stride >> 3);
         const float A = p.M.prop_a, B = p.M.prop_b;
+        /* The loads below keep only DBOT_STREAM_UNROLL x 32 B per thread in flight -- far too
+         * little for HBM latency.  One lane therefore runs a TMA prefetch (cp.async.bulk.prefetch.L2)
+         * DBOT_PREFETCH_AHEAD chunks ahead of the loop, across particle boundaries, so that the
+         * loads hit L2. */
+        constexpr int CHUNK8 = DBOT_ST * DBOT_STREAM_UNROLL;       /* 256-bit words per chunk */
+        const int n_chunks = (n8 + CHUNK8 - 1) / CHUNK8;
+        auto next_valid = [&](int i) { /* next particle of this CTA with a valid parent slot */
+            for (i += gridDim.x; i < p.n; i += gridDim.x)
+            {
+                const int sn = p.indices[i];
+                if (sn >= 0 && sn < p.n_slots) return i;
+            }
+            return -1;
+        };
+        auto prefetch_chunk = [&](const float* src, int c) {
+            const int q0 = c * CHUNK8;
+            const int nq = min(CHUNK8, n8 - q0);
+            if (nq > 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + ((size_t)q0 << 3)),
+                             "r"(nq * 32)
+                             : "memory");
+        };
+        bool first = true;
         for (int i = blockIdx.x; i < p.n; i += gridDim.x)
         {
             const int slot = p.indices[i];
             if (slot < 0 || slot >= p.n_slots) continue;
             const float* in = p.occ_in + (size_t)slot * p.slot_stride;
             float* out = p.occ_out + (size_t)i * p.slot_stride;
+            const float* in_next = nullptr;
+            if (sl == 0)
+            {
+                const int inext = next_valid(i);
+                if (inext >= 0) in_next = p.occ_in + (size_t)p.indices[inext] * p.slot_stride;
+                if (first)
+                    for (int c = 0; c < DBOT_PREFETCH_AHEAD; ++c) prefetch_chunk(in, c);
+            }
+            first = false;
 #ifdef DBOT_DBG_NO_STREAM
             if (p.n == 0x7654321)
 #endif
-            for (int base = sl; base < n8; base += DBOT_ST * DBOT_STREAM_UNROLL)
+            for (int c = 0; c < n_chunks; ++c)
             {
+                if (sl == 0)
+                {
+                    const int cp = c + DBOT_PREFETCH_AHEAD;
+                    if (cp < n_chunks)
+                        prefetch_chunk(in, cp);
+                    else if (in_next)
+                        prefetch_chunk(in_next, cp - n_chunks);
+                }
+                const int base = c * CHUNK8 + sl;
                 float v[DBOT_STREAM_UNROLL][8];
 #pragma unroll
                 for (int u = 0; u < DBOT_STREAM_UNROLL; ++u)
@@ -464,6 +531,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
     }
 
     /* ================= compute warps ================= */
+    if (MODE == DBOT_MODE_UPDATE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DBOT_COMPUTE_REGS));
     uint16_t* s_tri = (uint16_t*)(smem + p.off_tri);
     float4* s_v4 = (float4*)(smem + p.off_v4);
     int* s_Y = (int*)(smem + p.off_Y);
@@ -585,8 +653,8 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                     stage_chunk(0); /* resident after the first particle */
                     if (tid == 0) s_batch = 0;
                     compute_sync();
-                    dbot_raster_chunk(s_tri, p.chunks[0].n_tris, s_v4, s_Y, p.K, s_wt, &s_batch, rb0,
-                                      rb1, c0, c1, lane);
+                    dbot_raster_chunk(s_tri, p.chunks[0].n_tris, s_v4, s_Y, p.K, s_wt, s_owner_all[warp],
+                                      &s_batch, rb0, rb1, c0, c1, lane);
                 }
                 else
                 {
@@ -598,8 +666,8 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                         transform_chunk(ch, pose + 12 * ch.obj, d0, d1, d2, d3);
                         if (tid == 0) s_batch = 0;
                         compute_sync();
-                        dbot_raster_chunk(s_tri, ch.n_tris, s_v4, s_Y, p.K, s_wt, &s_batch, rb0, rb1,
-                                          c0, c1, lane);
+                        dbot_raster_chunk(s_tri, ch.n_tris, s_v4, s_Y, p.K, s_wt, s_owner_all[warp],
+                                          &s_batch, rb0, rb1, c0, c1, lane);
                     }
                 }
                 compute_sync();
@@ -610,59 +678,59 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                     role_arrive(DBOT_BAR_CONSUMED);
                     copied = true;
                 }
-                /* ---- per-pixel mixture over the band: a warp per row, 4 x 32 columns in flight ---- */
-#ifdef DBOT_DBG_NO_PIXELS
-                if (p.n == 0x7654321)
-#endif
-                for (int r = rb0 + warp; r <= rb1; r += DBOT_CW)
+                /* ---- per-pixel mixture over the band: a warp per row, DBOT_UNIT_PX x 32 columns
+                 * (and their loads) in flight per step ---- */
+                if (MODE == DBOT_MODE_RENDER)
                 {
-                    const uint32_t* wrow = s_wt + (r - rb0) * ww;
-                    const size_t grow = (size_t)r * p.pitch + c0;
-                    for (int cb = 0; cb < ww; cb += 128)
+                    for (int r = rb0 + warp; r <= rb1; r += DBOT_CW)
+                        for (int cc = lane; cc < ww; cc += 32)
+                            p.depth_out[(size_t)r * p.cols + c0 + cc] =
+                                dbot_depth_from_w(s_wt[(r - rb0) * ww + cc]);
+                }
+                else
+                {
+                    struct unit
                     {
-                        uint32_t wb[4];
-                        float4 tab[4];
-                        float o_in[4];
+                        uint32_t wb[DBOT_UNIT_PX];
+                        float4 tab[DBOT_UNIT_PX];
+                        float o_in[DBOT_UNIT_PX];
+                        size_t g; /* element offset of the unit's first column in the state / table */
+                    };
+                    auto fetch = [&](int r, int cb, unit& u) {
+                        const uint32_t* wrow = s_wt + (r - rb0) * ww + cb + lane;
+                        u.g = (size_t)r * p.pitch + c0 + cb + lane;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                        {
-                            const int cc = cb + 32 * j + lane;
-                            wb[j] = (cc < ww) ? wrow[cc] : DBOT_W_EMPTY;
-                        }
-                        if (MODE == DBOT_MODE_RENDER)
-                        {
+                        for (int j = 0; j < DBOT_UNIT_PX; ++j)
+                            u.wb[j] = (cb + 32 * j + lane < ww) ? wrow[32 * j] : DBOT_W_EMPTY;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
+                        for (int j = 0; j < DBOT_UNIT_PX; ++j)
+                            if (u.wb[j] != DBOT_W_EMPTY)
                             {
-                                const int cc = cb + 32 * j + lane;
-                                if (cc < ww)
-                                    p.depth_out[(size_t)r * p.cols + c0 + cc] = dbot_depth_from_w(wb[j]);
+                                u.tab[j] = __ldg(p.tab + u.g + 32 * j);
+                                u.o_in[j] = __ldg(occ_in + u.g + 32 * j);
                             }
-                            continue;
-                        }
+                    };
+                    auto evaluate = [&](const unit& u) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                        {
-                            const int cc = cb + 32 * j + lane;
-                            if (wb[j] != DBOT_W_EMPTY)
-                            {
-                                tab[j] = __ldg(p.tab + grow + cc);
-                                o_in[j] = __ldg(occ_in + grow + cc);
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                        {
-                            const int cc = cb + 32 * j + lane;
-                            if (wb[j] != DBOT_W_EMPTY && tab[j].x == tab[j].x)
+                        for (int j = 0; j < DBOT_UNIT_PX; ++j)
+                            if (u.wb[j] != DBOT_W_EMPTY && u.tab[j].x == u.tab[j].x)
                             {
                                 float o_new;
-                                acc = dbot_add(acc, dbot_pixel_term(dbot_rcp(dbot_u2f(wb[j])), tab[j],
-                                                                    o_in[j], p.M, o_new));
-                                if (MODE == DBOT_MODE_UPDATE) __stcs(occ_out + grow + cc, o_new);
+                                acc = dbot_add(acc, dbot_pixel_term(dbot_rcp(dbot_u2f(u.wb[j])), u.tab[j],
+                                                                    u.o_in[j], p.M, o_new));
+                                if (MODE == DBOT_MODE_UPDATE) __stcs(occ_out + u.g + 32 * j, o_new);
                             }
+                    };
+#ifdef DBOT_DBG_NO_PIXELS
+                    if (p.n == 0x7654321)
+#endif
+                    for (int r = rb0 + warp; r <= rb1; r += DBOT_CW)
+                        for (int cb = 0; cb < ww; cb += 32 * DBOT_UNIT_PX)
+                        {
+                            unit ua;
+                            fetch(r, cb, ua);
+                            evaluate(ua);
                         }
-                    }
                 }
             }
         }
@@ -928,7 +996,7 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     kp.off_v4 = off;  off += round_up((uint32_t)max_nv * 16u, 128);
     kp.off_Y = off;   off += round_up((uint32_t)max_nv * 4u, 128);
     kp.off_wt = off;
-    const int smem_max = (int)prop.sharedMemPerBlockOptin - 1024; /* static __shared__ + slack */
+    const int smem_max = (int)prop.sharedMemPerBlockOptin - 1024 - DBOT_CW * DBOT_OWNER_CAP; /* static __shared__ + slack */
     if ((int)off + 4 * (int)round_up((uint32_t)kp.cols, 4) > smem_max)
         return fail(-9, "image too wide for the shared-memory depth tile (cols=%d)", kp.cols);
     s->smem_bytes = smem_max;
