@@ -48,6 +48,9 @@
 #define DBOT_CHUNK_MAX_VERTS 3072
 #define DBOT_CHUNK_MAX_TRIS 6144
 #define DBOT_FULL 0xffffffffu
+#ifndef DBOT_RASTER_VARIANT
+#define DBOT_RASTER_VARIANT 0
+#endif
 #ifndef DBOT_UNIT_PX
 #define DBOT_UNIT_PX 4             /* pixels per lane and unit of the mixture pass */
 #endif
@@ -369,6 +372,7 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
             {
                 const float wr = dbot_fmaf(o_m1, fr, o_m2);
                 uint32_t bits[8], cur[8];
+#if DBOT_RASTER_VARIANT == 0
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc)
                 {
@@ -378,6 +382,31 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
                 }
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) dbot_tile_max_if(trow + 4u * cc, bits[cc], cur[cc]);
+#elif DBOT_RASTER_VARIANT == 1
+                uint32_t* prow = s_wt + ((trow - tile_s) >> 2);
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                {
+                    const int eor = (x0 + cc * o_e0c) | (x1 + cc * o_e1c) | (x2 + cc * o_e2c);
+                    bits[cc] = dbot_f2u(fminf(fmaxf(dbot_fmaf(o_m0, fc[cc], wr), o_wlo), o_whi));
+                    cur[cc] = eor >= 0 ? prow[cc] : 0xffffffffu;
+                }
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                    if (bits[cc] > cur[cc]) atomicMax(prow + cc, bits[cc]);
+#else
+                uint32_t* prow = s_wt + ((trow - tile_s) >> 2);
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                {
+                    const int eor = (x0 + cc * o_e0c) | (x1 + cc * o_e1c) | (x2 + cc * o_e2c);
+                    bits[cc] = dbot_f2u(fminf(fmaxf(dbot_fmaf(o_m0, fc[cc], wr), o_wlo), o_whi));
+                    cur[cc] = (uint32_t)eor;
+                }
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                    if ((int)cur[cc] >= 0) atomicMax(prow + cc, bits[cc]);
+#endif
                 x0 += o_e0r; x1 += o_e1r; x2 += o_e2r;
                 fr = dbot_add(fr, 1.0f);
                 trow += 4u * (uint32_t)ww;

@@ -1,0 +1,80 @@
+"""TEST INFRASTRUCTURE: one rank of the world_size-2 gloo test of dbot_ros_b200.sharded.  The local
+evaluator is the CPU oracle (tests may use it; the package never does) so that the host logic of
+the sharded sensor -- shard bounds, global->local parent slots, ragged all-gather, state hand-over
+-- runs on a machine without GPUs."""
+import os
+import sys
+
+import numpy as np
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import oracle_lib  # noqa: E402
+from dbot_ros_b200 import synth  # noqa: E402
+from dbot_ros_b200.sharded import CrossShardParent, ShardedRbSensor, shard_bounds  # noqa: E402
+
+
+def scenario(n, frames, seed):
+    """inputs every rank (and the single-process check) rebuilds identically"""
+    rows, cols = synth.resolution(8)
+    K = synth.camera_matrix(8)
+    V, T = synth.mesh_set("ico80")
+    rng = np.random.default_rng(seed)
+    gt = synth.ground_truth_poses(1, rng)
+    return rows, cols, K, V, T, rng, gt
+
+
+def shard_local_parents(n, world, rng):
+    """resampling that keeps every parent inside its child's shard (BASELINE config 4)"""
+    out = np.empty(n, dtype=np.int32)
+    for r in range(world):
+        lo, hi = shard_bounds(n, world, r)
+        out[lo:hi] = rng.integers(lo, hi, size=hi - lo)
+    return out
+
+
+def run(sensor, n, frames, world, seed, render):
+    rows, cols, K, V, T, rng, gt = scenario(n, frames, seed)
+    idx = np.zeros(n, dtype=np.int32)
+    outs = []
+    for f in range(frames):
+        frame = synth.make_frame(render, gt, rows, cols, rng)
+        poses = synth.particle_poses(gt, n, rng)
+        if f > 0:
+            idx = shard_local_parents(n, world, rng)
+        sensor.set_observation(frame)
+        outs.append(sensor.loglikes_poses(poses, idx, update=False))
+        outs.append(sensor.loglikes_poses(poses, idx, update=True))
+        assert np.array_equal(idx, np.arange(n))
+    return np.stack(outs)
+
+
+def main():
+    out_path, n, frames, seed = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rows, cols, K, V, T, _, _ = scenario(n, frames, seed)
+    local = oracle_lib.Oracle(rows, cols, K, V, T, synth.default_parameters())
+    sensor = ShardedRbSensor(local)
+    got = run(sensor, n, frames, world, seed, local.render)
+    # a parent on the other rank must be refused, not silently evaluated
+    refused = False
+    bad = np.arange(n, dtype=np.int32)[::-1].copy()
+    try:
+        sensor.loglikes_poses(np.zeros((n, 1, 12), np.float32), bad, update=False)
+    except CrossShardParent:
+        refused = True
+    flags = [None] * world
+    dist.all_gather_object(flags, refused)
+    sensor.reset()
+    assert sensor.n_slots == 1
+    np.savez(out_path + ".rank%d.npz" % rank, got=got, refused=np.array(flags), lo_hi=np.array(shard_bounds(n, world, rank)),
+             local_slots=local.n_slots)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
