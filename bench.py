@@ -73,27 +73,54 @@ def make_inputs(w, render, rank):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)"""
+    """SM clock + throttle reasons DURING the timed region, read through NVML every 2 ms (an
+    nvidia-smi process takes longer to start than a timed region lasts); falls back to nvidia-smi."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index, self.samples, self.stop = index, [], threading.Event()
         self.thread = threading.Thread(target=self.run, daemon=True)
+        self.nvml = None
+        self.sm_max = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            try:
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            return mhz, mask
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=5).stdout.strip().split(",")
+        self.sm_max = float(out[1])
+        mask = sum(bit for (nm, bit), v in zip(self.REASONS, out[2:6]) if v.strip() == "Active")
+        return float(out[0]), mask
 
     def run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self.samples.append(self.sample())
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.002 if self.nvml is not None else 0.1)
 
     def __enter__(self):
         self.thread.start()
@@ -105,17 +132,19 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for k, nm in enumerate(names) if any(s[2 + k] == "Active" for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["clock query unavailable"]}
+        sm = sorted(m for m, _ in self.samples)
+        mask = 0
+        for _, k in self.samples:
+            mask |= k
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max,
+                "reasons": [nm for nm, bit in self.REASONS if mask & bit], "samples": len(self.samples),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def cpu_oracle_rate(w, frames, poses, sample, reps, threads=None):
-    """oracle on the host cores: set_observation + loglikes(update) on `sample` particles"""
+def cpu_oracle_rate(w, frames, poses, sample, reps, threads=None, min_seconds=0.0, max_reps=None):
+    """oracle on the host cores: set_observation + loglikes(update) on `sample` particles per step;
+    runs `reps` steps, then keeps going until `min_seconds` of CPU work have been timed"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
 
@@ -126,14 +155,16 @@ def cpu_oracle_rate(w, frames, poses, sample, reps, threads=None):
     orc.set_observation(frames[0])
     orc.loglikes_poses(poses[0][:sample], idx, True)  # warm-up, leaves `sample` slots
     times = []
-    for r in range(reps):
+    r = 0
+    while r < reps or (sum(times) < min_seconds and (max_reps is None or r < max_reps)):
         f = r % N_FRAMES
         t0 = time.perf_counter()
         orc.set_observation(frames[f])
         orc.loglikes_poses(poses[f][:sample], idx, True)
         times.append(time.perf_counter() - t0)
+        r += 1
     orc.close()
-    return sample / float(np.mean(times)), cores, float(np.mean(times))
+    return sample / float(np.mean(times)), cores, float(np.mean(times)), len(times)
 
 
 def run_reference(args):
@@ -150,16 +181,18 @@ def run_reference(args):
     orc = oracle_lib.Oracle(w["rows"], w["cols"], w["K"], w["V"], w["T"], synth.default_parameters())
     _, frames, poses, _ = make_inputs(w, orc.render, 0)
     orc.close()
-    sample = 64
-    cores = os.cpu_count() or 1
+    sample = min(w["n"], 250)           # bounded sample of the step's particles: ~0.1 s of CPU work per step
     cpu_oracle_rate(w, frames, poses, sample, max(args.warmup, 1))
-    rate, cores, sec = cpu_oracle_rate(w, frames, poses, sample, args.steps)
+    rate, cores, sec, _ = cpu_oracle_rate(w, frames, poses, sample, args.steps)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": describe(w, args.gpus),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d of the %d particles per step, same frames" % (sample, w["n"])},
+                             "sample": "%d of the %d particles per step, same frames, OpenMP over particles"
+                                       % (sample, w["n"]),
+                             "why_port": "the reference's evaluator lives in the un-vendored dbot library "
+                                         "(needs Eigen 3.2, fl, catkin): not buildable here, see DESIGN.md"},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -167,7 +200,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -245,18 +278,33 @@ def main():
 
     # ---- e2e: host buffers through the reference-facing call ----
     idx_host = [p.copy() for p in parents]
+    if world > 1:
+        # the public multi-GPU API: particle-sharded sensor, all-gather of log-weights inside the call.
+        # Every rank passes the global arrays; it reads only its own contiguous shard of them.
+        from dbot_ros_b200.sharded import ShardedRbSensor, shard_bounds
+
+        sharded = ShardedRbSensor(sensor)
+        sharded.n_slots = n * world                   # the warm-up above left n slots on every rank
+        lo, hi = shard_bounds(n * world, world, rank)
+        g_poses, g_parents = [], []
+        for f in range(N_FRAMES):
+            gp = np.zeros((n * world,) + poses[f].shape[1:], dtype=np.float32)
+            gp[lo:hi] = poses[f]
+            gi = np.arange(n * world, dtype=np.int32)
+            gi[lo:hi] = parents[f] + lo                # shard-local parents (BASELINE config 4)
+            g_poses.append(gp)
+            g_parents.append(gi)
+        g_idx = [g.copy() for g in g_parents]
 
     def host_step(k):
         f = k % N_FRAMES
+        if world > 1:
+            g_idx[f][:] = g_parents[f]
+            sharded.set_observation(frames[f])
+            return sharded.loglikes_poses(g_poses[f], g_idx[f], True)
         idx_host[f][:] = parents[f]
         sensor.set_observation(frames[f])
-        out = sensor.loglikes_poses(poses[f], idx_host[f], True)
-        if world > 1:
-            with torch.cuda.stream(ext):
-                d_out.copy_(torch.from_numpy(out), non_blocking=True)
-                dist.all_gather_into_tensor(d_all, d_out)
-            ext.synchronize()
-            d_all.cpu()
+        return sensor.loglikes_poses(poses[f], idx_host[f], True)
 
     for k in range(args.warmup):
         host_step(k)
@@ -310,11 +358,11 @@ def main():
             "gpu_launches": gpu_launches, "clocks": clocks.summary(), "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = 64
-        rate, cores, sec = cpu_oracle_rate(w, frames, poses, sample, reps=6)
+        sample = min(n, 250)
+        rate, cores, sec, reps = cpu_oracle_rate(w, frames, poses, sample, reps=4, min_seconds=12.0, max_reps=400)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "%d of the %d particles, 6 frames, %.2f s per frame"
-                                          % (sample, n, sec)}
+                                "sample": "%d of the %d particles per step, %d steps (%.1f s of CPU work), same "
+                                          "frames, OpenMP over particles" % (sample, n, reps, sec * reps)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
