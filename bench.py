@@ -277,6 +277,10 @@ def main():
     value = n * world * args.steps / (ms * 1e-3)
 
     # ---- e2e: host buffers through the reference-facing call ----
+    # the step's inputs start in page-locked host memory (the library copies straight from it)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    frames = [pin(f) for f in frames]
+    poses = [pin(q) for q in poses]
     idx_host = [p.copy() for p in parents]
     if world > 1:
         # the public multi-GPU API: particle-sharded sensor, all-gather of log-weights inside the call.

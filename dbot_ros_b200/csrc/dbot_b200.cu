@@ -844,7 +844,8 @@ struct dbot_b200_sensor
     int cur, n_slots;
     double t_obs, t_update;
     /* measurement */
-    cudaEvent_t ev_begin, ev_end, ev_k0, ev_k1;
+    cudaEvent_t ev_begin, ev_end, ev_k0, ev_k1, ev_obs;
+    int obs_in_flight; /* the staged depth frame may still be on its way to the device */
     int profile;
     float prof_ms[DBOT_B200_KERNEL_COUNT];
     int64_t prof_launches[DBOT_B200_KERNEL_COUNT];
@@ -947,6 +948,7 @@ extern "C" int dbot_b200_destroy(dbot_b200_sensor* s)
     if (s->ev_end) cudaEventDestroy(s->ev_end);
     if (s->ev_k0) cudaEventDestroy(s->ev_k0);
     if (s->ev_k1) cudaEventDestroy(s->ev_k1);
+    if (s->ev_obs) cudaEventDestroy(s->ev_obs);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return 0;
@@ -974,6 +976,7 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     CUDA_TRY(cudaEventCreate(&s->ev_end));
     CUDA_TRY(cudaEventCreate(&s->ev_k0));
     CUDA_TRY(cudaEventCreate(&s->ev_k1));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_obs, cudaEventDisableTiming));
 
     /* mesh */
     std::vector<dbot_chunk> chunks;
@@ -1147,18 +1150,42 @@ static int launch_observation(dbot_b200_sensor* s, const float* d_depth)
     return 0;
 }
 
+/* page-locked host memory can be handed to the copy engine as it is */
+static bool is_pinned_host(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 /* RbSensor::set_observation */
 extern "C" int dbot_b200_set_observation(dbot_b200_sensor* s, const float* depth_m)
 {
     if (!s || !depth_m) return fail(-1, "set_observation: null argument");
     CUDA_TRY(cudaSetDevice(s->device));
     const size_t bytes = (size_t)s->kp.rows * s->kp.cols * sizeof(float);
+    if (is_pinned_host(depth_m))
+    {
+        /* the caller's buffer is page-locked: copy straight from it, and be done with it on return */
+        CUDA_TRY(cudaMemcpyAsync(s->d_obs, depth_m, bytes, cudaMemcpyHostToDevice, s->stream));
+        int rc = launch_observation(s, s->d_obs);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        return 0;
+    }
+    /* pageable: stage in the handle's own pinned buffer; the copy and the table kernel are left
+     * running -- every later call on this handle is ordered behind them on the same stream, and the
+     * staging buffer is not touched again before they are done */
+    if (s->obs_in_flight) CUDA_TRY(cudaEventSynchronize(s->ev_obs));
     memcpy(s->h_obs, depth_m, bytes);
     CUDA_TRY(cudaMemcpyAsync(s->d_obs, s->h_obs, bytes, cudaMemcpyHostToDevice, s->stream));
-    int rc = launch_observation(s, s->d_obs);
-    if (rc) return rc;
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return 0;
+    CUDA_TRY(cudaEventRecord(s->ev_obs, s->stream));
+    s->obs_in_flight = 1;
+    return launch_observation(s, s->d_obs);
 }
 
 extern "C" int dbot_b200_set_observation_device(dbot_b200_sensor* s, const float* d_depth_m)
