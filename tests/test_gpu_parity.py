@@ -217,3 +217,73 @@ def test_full_size_properties():
     second = sensor.loglikes_poses(poses[pick], pick.astype(np.int32), False)
     want2 = orc.loglikes_poses(poses[pick], np.arange(16, dtype=np.int32), False)
     assert rel_err(second, want2) < REL_TOL
+
+
+def test_config3_roofline_size_properties():
+    """BASELINE config 3 (10 000 particles, 640x480, 5120 triangles; 24.6 GB of occlusion state):
+    too big for the oracle, so size-independent properties -- update leaves the weights of its own
+    call unchanged, chunked evaluation equals whole evaluation bit for bit, identity parents after
+    the update -- plus an oracle spot check on 8 particles drawn from all over the index range."""
+    n = 10000
+    sensor, orc, rows, cols, n_obj = make_pair("icosphere5k", 1, n)
+    rng = synth.rng_for(3)
+    gt = synth.ground_truth_poses(n_obj, rng)
+    frame = synth.make_frame(sensor.render, gt, rows, cols, rng)
+    poses = synth.particle_poses(gt, n, rng)
+    sensor.set_observation(frame)
+    idx = np.zeros(n, dtype=np.int32)
+    whole = sensor.loglikes_poses(poses, idx, False)
+    parts = np.concatenate([sensor.loglikes_poses(poses[a:a + 2500], idx[a:a + 2500].copy(), False)
+                            for a in range(0, n, 2500)])
+    assert np.array_equal(whole, parts)
+    upd = sensor.loglikes_poses(poses, idx, True)
+    assert np.array_equal(upd, whole) and np.array_equal(idx, np.arange(n)) and sensor.n_slots == n
+    pick = np.sort(rng.choice(n, 8, replace=False))
+    orc.set_observation(frame)
+    io = np.zeros(8, dtype=np.int32)
+    want = orc.loglikes_poses(poses[pick], io, True)
+    assert rel_err(whole[pick], want) < REL_TOL
+    # second frame: parents = a resampling of all 10 000 slots; spot check against the oracle,
+    # whose slots 0..7 now hold the picked particles' images
+    frame2 = synth.make_frame(sensor.render, gt, rows, cols, rng)
+    sensor.set_observation(frame2)
+    orc.set_observation(frame2)
+    parents = rng.integers(0, n, size=n).astype(np.int32)
+    parents[pick] = pick                      # the picked particles keep their own history
+    got2 = sensor.loglikes_poses(poses, parents, True)
+    want2 = orc.loglikes_poses(poses[pick], np.arange(8, dtype=np.int32), True)
+    assert rel_err(got2[pick], want2) < REL_TOL
+    for k in (0, 7):
+        assert np.max(np.abs(sensor.occlusion(int(pick[k])) - orc.occlusion(k))) < 2 * OCC_TOL
+
+
+def test_observation_paths_pinned_and_staged():
+    """set_observation copies straight from page-locked caller memory and stages pageable memory
+    asynchronously; both must behave like a synchronous copy (the caller may reuse its buffer)."""
+    import torch
+
+    n = 32
+    sensor, orc, rows, cols, n_obj = make_pair("uvsphere480", 4, n)
+    rng = synth.rng_for(1)
+    gt = synth.ground_truth_poses(n_obj, rng)
+    poses = synth.particle_poses(gt, n, rng)
+    f1 = synth.make_frame(orc.render, gt, rows, cols, rng)
+    f2 = synth.make_frame(orc.render, gt, rows, cols, rng)
+    orc.set_observation(f1)
+    orc.set_observation(f2)                          # two frames in a row: time advances twice
+    want = orc.loglikes_poses(poses, np.zeros(n, np.int32), False)
+    buf = f1.copy()                                  # pageable
+    sensor.set_observation(buf)
+    buf[:] = np.nan                                  # reuse at once: the staged copy must be unaffected
+    pinned = torch.from_numpy(f2.copy()).pin_memory().numpy()
+    sensor.set_observation(pinned)
+    pinned[:] = np.nan
+    got = sensor.loglikes_poses(poses, np.zeros(n, np.int32), False)
+    assert abs(sensor.observation_time - orc.observation_time) < 1e-12
+    assert rel_err(got, want) < REL_TOL
+    sensor.set_observation(f1)
+    sensor.set_observation(f2)                       # staged twice in a row
+    orc.set_observation(f1)
+    orc.set_observation(f2)
+    assert rel_err(sensor.loglikes_poses(poses, np.zeros(n, np.int32), False),
+                   orc.loglikes_poses(poses, np.zeros(n, np.int32), False)) < REL_TOL
