@@ -173,6 +173,25 @@ def rotation_matrices(euler_vectors):
     return np.where((angle > 0.0)[..., None, None], R, ident)
 
 
+def compose_poses(deltas, default_poses):
+    """pose = delta (x) default for every particle and object: t = t_delta + t_default,
+    R = R_delta R_default, in double, then rounded to the float32 [n][n_objects][12] (R row-major, t)
+    the C-ABI takes.  deltas: [n, n_objects*12] FreeFloatingRigidBodiesState or [n, n_objects*6]."""
+    default_poses = np.asarray(default_poses, dtype=np.float64).reshape(-1, 6)
+    n_obj = default_poses.shape[0]
+    d = np.asarray(deltas, dtype=np.float64)
+    n = d.shape[0]
+    d = d.reshape(n, n_obj, -1)
+    if d.shape[2] not in (6, 12):
+        raise ValueError("loglikes: states must have 6 or 12 numbers per object")
+    R = rotation_matrices(d[:, :, 3:6]) @ rotation_matrices(default_poses[:, 3:6])[None]
+    t = d[:, :, 0:3] + default_poses[None, :, 0:3]
+    out = np.empty((n, n_obj, 12), dtype=np.float32)
+    out[:, :, :9] = R.reshape(n, n_obj, 9)
+    out[:, :, 9:] = t
+    return out
+
+
 class RbSensor:
     """dbot::RbSensor<State> (model/rb_sensor.h): the interface the particle filter drives."""
 
@@ -238,19 +257,7 @@ class B200KinectImageModel(RbSensor):
         self._default_poses = np.asarray(poses, dtype=np.float64).reshape(self.n_objects, 6).copy()
 
     def compose(self, deltas):
-        """pose = delta (x) default: t = t_delta + t_default, R = R_delta R_default, in double,
-        then rounded to the float32 [n][n_objects][12] (R row-major, t) the C-ABI takes."""
-        d = np.asarray(deltas, dtype=np.float64)
-        n = d.shape[0]
-        d = d.reshape(n, self.n_objects, -1)
-        if d.shape[2] not in (6, 12):
-            raise ValueError("loglikes: states must have 6 or 12 numbers per object")
-        R = rotation_matrices(d[:, :, 3:6]) @ rotation_matrices(self._default_poses[:, 3:6])[None]
-        t = d[:, :, 0:3] + self._default_poses[None, :, 0:3]
-        out = np.empty((n, self.n_objects, 12), dtype=np.float32)
-        out[:, :, :9] = R.reshape(n, self.n_objects, 9)
-        out[:, :, 9:] = t
-        return out
+        return compose_poses(deltas, self._default_poses)
 
     def loglikes_poses(self, poses, indices, update=False):
         poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, self.n_objects, 12)
