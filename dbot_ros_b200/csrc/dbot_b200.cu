@@ -79,9 +79,13 @@ struct dbot_kparams
     const dbot_chunk* chunks;
     const unsigned char* mesh;
     const float4* tab;      /* [rows*pitch] observation table */
-    const float* occ_in;    /* [n_slots][slot_stride] */
-    float* occ_out;         /* [n][slot_stride] (update) */
+    float* pool;            /* [2 * max_particles][slot_stride] physical occlusion slots */
+    const int32_t* loc;     /* [n_slots] logical slot -> physical slot (current generation) */
+    const int4* plan;       /* update: per particle { source slot, destination slot, parent, 0 } (physical) */
+    const int32_t* order;   /* update: processing order, copying children before adopting ones */
+    int32_t* pending;       /* update: per parent, copies of its image still to be read */
     size_t slot_stride;     /* rows*pitch */
+    float post_b, post_inv_a; /* update: the posterior o is stored as (o - post_b) * post_inv_a */
     const float* poses;     /* [n][n_obj][12] */
     int32_t* indices;       /* [n] */
     double* out;            /* [n] */
@@ -204,6 +208,141 @@ __global__ void dbot_fill_kernel(float* __restrict__ dst, size_t n, float v)
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) dst[i] = v;
+}
+
+/* rebase of the lazily propagated state: stored <- A * stored + B in every live slot (rare: once the
+ * accumulated factor A has shrunk to 2^-60, i.e. after roughly 80 s of tracking) */
+__global__ void dbot_rebase_kernel(float* __restrict__ pool, const int32_t* __restrict__ loc, int n_slots,
+                                   size_t slot_stride, float A, float B)
+{
+    for (int sidx = blockIdx.y; sidx < n_slots; sidx += gridDim.y)
+    {
+        float* dst = pool + (size_t)loc[sidx] * slot_stride;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < slot_stride;
+             i += (size_t)gridDim.x * blockDim.x)
+            dst[i] = __fmaf_rn(A, dst[i], B);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Update planning (one CTA).  dbot's update gives every particle a new occlusion image: a copy of
+ * its parent's, with the covered pixels replaced.  Copying 4*P bytes per particle is the HBM cost
+ * of the path, and half of it is avoidable: the LAST child of every parent simply adopts the
+ * parent's physical slot (nothing else will ever read that parent again), only the other children
+ * get a fresh slot and a copy.  Without resampling (parents = identity) nothing is copied at all.
+ * Physical slots live in a pool of 2 * max_particles; `loc` maps logical slot -> physical slot;
+ * `free_stack` holds the unused ones.  Outputs: plan[i] = { source, destination, parent, 0 },
+ * order[] = copying children first (so that an adopting child never waits for a copy that has not
+ * been scheduled yet), pending[parent] = number of copies that must read the parent before the
+ * adopting child may write into it, loc_next[i] = destination. */
+#define DBOT_PLAN_THREADS 1024
+__device__ __forceinline__ int dbot_block_exclusive_scan(int v, int* s_warp, int* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const int o = __shfl_up_sync(DBOT_FULL, inc, d);
+        if (lane >= d) inc += o;
+    }
+    __syncthreads(); /* s_warp may still be read from a previous scan */
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0)
+    {
+        const int w = s_warp[lane];
+        int winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const int o = __shfl_up_sync(DBOT_FULL, winc, d);
+            if (lane >= d) winc += o;
+        }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return s_warp[warp] + inc - v;
+}
+
+__global__ void __launch_bounds__(DBOT_PLAN_THREADS, 1)
+    dbot_plan_update_kernel(const int32_t* __restrict__ parents, int n, int n_slots,
+                            const int32_t* __restrict__ loc, int32_t* __restrict__ loc_next,
+                            int32_t* __restrict__ free_stack, int32_t* __restrict__ free_count,
+                            int32_t* __restrict__ cnt, int32_t* __restrict__ last,
+                            int32_t* __restrict__ pending, int32_t* __restrict__ order,
+                            int4* __restrict__ plan, int* __restrict__ err_flag)
+{
+    __shared__ int s_warp[33];
+    const int t = threadIdx.x;
+    for (int sidx = t; sidx < n_slots; sidx += DBOT_PLAN_THREADS)
+    {
+        cnt[sidx] = 0;
+        last[sidx] = -1;
+    }
+    __syncthreads();
+    for (int i = t; i < n; i += DBOT_PLAN_THREADS)
+    {
+        const int par = parents[i];
+        if (par >= 0 && par < n_slots)
+        {
+            atomicAdd(cnt + par, 1);
+            atomicMax(last + par, i);
+        }
+        else
+            atomicExch(err_flag, 1);
+    }
+    __syncthreads();
+    /* contiguous ranges per thread keep the order of copies and adoptions stable */
+    const int per = (n + DBOT_PLAN_THREADS - 1) / DBOT_PLAN_THREADS;
+    const int i0 = min(t * per, n), i1 = min(i0 + per, n);
+    int copies = 0, adopts = 0;
+    for (int i = i0; i < i1; ++i)
+    {
+        const int par = parents[i];
+        const bool ok = par >= 0 && par < n_slots;
+        if (ok && last[par] == i) ++adopts; else ++copies; /* an orphan takes a fresh slot, unfilled */
+    }
+    int n_copies, n_adopts;
+    int crank = dbot_block_exclusive_scan(copies, s_warp, &n_copies);
+    int arank = dbot_block_exclusive_scan(adopts, s_warp, &n_adopts);
+    const int f0 = *free_count;
+    for (int i = i0; i < i1; ++i)
+    {
+        const int par = parents[i];
+        const bool ok = par >= 0 && par < n_slots;
+        int4 pl;
+        if (ok && last[par] == i)
+        {
+            pl = make_int4(loc[par], loc[par], par, 0);
+            order[n_copies + arank++] = i;
+        }
+        else
+        {
+            pl = make_int4(ok ? loc[par] : -1, free_stack[f0 - 1 - crank], ok ? par : 0, 0);
+            order[crank++] = i;
+        }
+        plan[i] = pl;
+        loc_next[i] = pl.y;
+    }
+    /* parents without children give their slots back */
+    const int pers = (n_slots + DBOT_PLAN_THREADS - 1) / DBOT_PLAN_THREADS;
+    const int s0 = min(t * pers, n_slots), s1 = min(s0 + pers, n_slots);
+    int freed = 0;
+    for (int sidx = s0; sidx < s1; ++sidx) freed += (cnt[sidx] == 0);
+    int n_freed;
+    int frank = dbot_block_exclusive_scan(freed, s_warp, &n_freed);
+    __syncthreads(); /* every thread has taken its fresh slots from the top of the stack */
+    for (int sidx = s0; sidx < s1; ++sidx)
+    {
+        if (cnt[sidx] == 0)
+            free_stack[f0 - n_copies + frank++] = loc[sidx];
+        pending[sidx] = max(cnt[sidx] - 1, 0);
+    }
+    __syncthreads();
+    if (t == 0) *free_count = f0 - n_copies + n_freed;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -474,24 +613,25 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
     }
     __syncthreads();
 
-    /* ================= streaming warps (update launches only) ================= */
+    /* ================= streaming warps (update launches only) =================
+     * A child that does not adopt its parent's slot (see dbot_plan_update_kernel) starts as a bit
+     * copy of the parent's stored image; propagation is applied lazily (dbot_b200_sensor::A). */
     if (MODE == DBOT_MODE_UPDATE && warp >= DBOT_CW)
     {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DBOT_STREAM_REGS));
         const int sl = tid - DBOT_CT;
         const int n8 = (int)(p.slot_stride >> 3);
-        const float A = p.M.prop_a, B = p.M.prop_b;
         /* The loads below keep only DBOT_STREAM_UNROLL x 32 B per thread in flight -- far too
          * little for HBM latency.  One lane therefore runs a TMA prefetch (cp.async.bulk.prefetch.L2)
          * DBOT_PREFETCH_AHEAD chunks ahead of the loop, across particle boundaries, so that the
          * loads hit L2. */
         constexpr int CHUNK8 = DBOT_ST * DBOT_STREAM_UNROLL;       /* 256-bit words per chunk */
         const int n_chunks = (n8 + CHUNK8 - 1) / CHUNK8;
-        auto next_valid = [&](int i) { /* next particle of this CTA with a valid parent slot */
-            for (i += gridDim.x; i < p.n; i += gridDim.x)
+        auto next_copy = [&](int k) { /* source of the next copying child of this CTA */
+            for (k += gridDim.x; k < p.n; k += gridDim.x)
             {
-                const int sn = p.indices[i];
-                if (sn >= 0 && sn < p.n_slots) return i;
+                const int4 pl = p.plan[p.order[k]];
+                if (pl.x >= 0 && pl.x != pl.y) return pl.x;
             }
             return -1;
         };
@@ -504,51 +644,49 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                              : "memory");
         };
         bool first = true;
-        for (int i = blockIdx.x; i < p.n; i += gridDim.x)
+        for (int k = blockIdx.x; k < p.n; k += gridDim.x)
         {
-            const int slot = p.indices[i];
-            if (slot < 0 || slot >= p.n_slots) continue;
-            const float* in = p.occ_in + (size_t)slot * p.slot_stride;
-            float* out = p.occ_out + (size_t)i * p.slot_stride;
-            const float* in_next = nullptr;
-            if (sl == 0)
+            const int4 pl = p.plan[p.order[k]];
+            if (pl.x < 0) continue;
+            if (pl.x != pl.y)
             {
-                const int inext = next_valid(i);
-                if (inext >= 0) in_next = p.occ_in + (size_t)p.indices[inext] * p.slot_stride;
-                if (first)
-                    for (int c = 0; c < DBOT_PREFETCH_AHEAD; ++c) prefetch_chunk(in, c);
-            }
-            first = false;
-#ifdef DBOT_DBG_NO_STREAM
-            if (p.n == 0x7654321)
-#endif
-            for (int c = 0; c < n_chunks; ++c)
-            {
+                const float* in = p.pool + (size_t)pl.x * p.slot_stride;
+                float* out = p.pool + (size_t)pl.y * p.slot_stride;
+                const float* in_next = nullptr;
                 if (sl == 0)
                 {
-                    const int cp = c + DBOT_PREFETCH_AHEAD;
-                    if (cp < n_chunks)
-                        prefetch_chunk(in, cp);
-                    else if (in_next)
-                        prefetch_chunk(in_next, cp - n_chunks);
+                    const int snext = next_copy(k);
+                    if (snext >= 0) in_next = p.pool + (size_t)snext * p.slot_stride;
+                    if (first)
+                        for (int c = 0; c < DBOT_PREFETCH_AHEAD; ++c) prefetch_chunk(in, c);
                 }
-                const int base = c * CHUNK8 + sl;
-                float v[DBOT_STREAM_UNROLL][8];
-#pragma unroll
-                for (int u = 0; u < DBOT_STREAM_UNROLL; ++u)
+                first = false;
+#ifdef DBOT_DBG_NO_STREAM
+                if (p.n == 0x7654321)
+#endif
+                for (int c = 0; c < n_chunks; ++c)
                 {
-                    const int q = base + u * DBOT_ST;
-                    if (q < n8) ldg256(in + ((size_t)q << 3), v[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < DBOT_STREAM_UNROLL; ++u)
-                {
-                    const int q = base + u * DBOT_ST;
-                    if (q < n8)
+                    if (sl == 0)
                     {
+                        const int cp = c + DBOT_PREFETCH_AHEAD;
+                        if (cp < n_chunks)
+                            prefetch_chunk(in, cp);
+                        else if (in_next)
+                            prefetch_chunk(in_next, cp - n_chunks);
+                    }
+                    const int base = c * CHUNK8 + sl;
+                    float v[DBOT_STREAM_UNROLL][8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[u][e] = dbot_fmaf(A, v[u][e], B);
-                        stg256_stream(out + ((size_t)q << 3), v[u]);
+                    for (int u = 0; u < DBOT_STREAM_UNROLL; ++u)
+                    {
+                        const int q = base + u * DBOT_ST;
+                        if (q < n8) ldg256(in + ((size_t)q << 3), v[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < DBOT_STREAM_UNROLL; ++u)
+                    {
+                        const int q = base + u * DBOT_ST;
+                        if (q < n8) stg256_stream(out + ((size_t)q << 3), v[u]);
                     }
                 }
             }
@@ -604,25 +742,32 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
         }
     };
 
-    for (int i = blockIdx.x; i < p.n; i += gridDim.x)
+    for (int k = blockIdx.x; k < p.n; k += gridDim.x)
     {
+        /* update launches walk the particles in the planned order (copying children first) */
+        const int i = (MODE == DBOT_MODE_UPDATE) ? p.order[k] : k;
         const float* pose = p.poses + (size_t)i * 12 * p.n_obj;
-        int slot = 0;
-        if (MODE != DBOT_MODE_RENDER)
+        int4 pl = make_int4(0, 0, 0, 0);
+        if (MODE == DBOT_MODE_UPDATE)
+            pl = p.plan[i];
+        else if (MODE == DBOT_MODE_EVAL)
         {
-            slot = p.indices[i];
-            if (slot < 0 || slot >= p.n_slots)
-            {
-                if (tid == 0)
-                {
-                    p.out[i] = __longlong_as_double(0x7ff8000000000000LL);
-                    atomicExch(p.err_flag, 1);
-                }
-                continue;
-            }
+            const int slot = p.indices[i];
+            pl.x = (slot < 0 || slot >= p.n_slots) ? -1 : p.loc[slot];
         }
-        const float* occ_in = p.occ_in + (size_t)slot * p.slot_stride;
-        float* occ_out = (MODE == DBOT_MODE_UPDATE) ? p.occ_out + (size_t)i * p.slot_stride : nullptr;
+        if (pl.x < 0)
+        {
+            if (tid == 0)
+            {
+                p.out[i] = __longlong_as_double(0x7ff8000000000000LL);
+                atomicExch(p.err_flag, 1);
+            }
+            continue;
+        }
+        /* stored occlusion values are read from the parent's slot; an adopting sibling leaves it
+         * alone until this particle has signed off (pending count, end of the particle) */
+        const float* occ_in = p.pool + (size_t)pl.x * p.slot_stride;
+        float* occ_out = (MODE == DBOT_MODE_UPDATE) ? p.pool + (size_t)pl.y * p.slot_stride : nullptr;
 
         /* ---- pass 1: transform every chunk, collect the screen window of the particle ---- */
         if (tid == 0)
@@ -662,7 +807,24 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
         const bool have_window = (c0 <= c1) && (r0 <= r1);
         const int ww = c1 - c0 + 1;
         float acc = 0.0f;
-        bool copied = false; /* update: the streamed copy of this particle has been awaited */
+        bool copied = false; /* update: this particle's slot is ready for the posterior */
+        auto await_slot = [&]() {
+            /* a copying child: its slot holds the parent's image once the streaming warps arrive.
+             * An adopting child owns the parent's slot itself and waits until all its siblings are
+             * done reading it (they sign off at the end of their particle). */
+            role_sync(DBOT_BAR_COPIED);
+            role_arrive(DBOT_BAR_CONSUMED);
+            if (pl.x == pl.y)
+            {
+                if (tid == 0)
+                {
+                    while (atomicAdd(p.pending + pl.z, 0) > 0) __nanosleep(200);
+                    __threadfence();
+                }
+                compute_sync();
+            }
+            copied = true;
+        };
 
         if (have_window)
         {
@@ -700,13 +862,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                     }
                 }
                 compute_sync();
-                if (MODE == DBOT_MODE_UPDATE && !copied)
-                {
-                    /* the child's slot now holds the propagated parent image everywhere */
-                    role_sync(DBOT_BAR_COPIED);
-                    role_arrive(DBOT_BAR_CONSUMED);
-                    copied = true;
-                }
+                if (MODE == DBOT_MODE_UPDATE && !copied) await_slot();
                 /* ---- per-pixel mixture over the band: a warp per row, DBOT_UNIT_PX x 32 columns
                  * (and their loads) in flight per step ---- */
                 if (MODE == DBOT_MODE_RENDER)
@@ -736,7 +892,10 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                             if (u.wb[j] != DBOT_W_EMPTY)
                             {
                                 u.tab[j] = __ldg(p.tab + u.g + 32 * j);
-                                u.o_in[j] = __ldg(occ_in + u.g + 32 * j);
+                                /* update launches may read a slot whose covered pixels were written
+                                 * in an earlier launch phase by its adopter-to-be: L2-coherent, not .nc */
+                                u.o_in[j] = (MODE == DBOT_MODE_UPDATE) ? __ldcg(occ_in + u.g + 32 * j)
+                                                                       : __ldg(occ_in + u.g + 32 * j);
                             }
                     };
                     auto evaluate = [&](const unit& u) {
@@ -747,7 +906,8 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                                 float o_new;
                                 acc = dbot_add(acc, dbot_pixel_term(dbot_rcp(dbot_u2f(u.wb[j])), u.tab[j],
                                                                     u.o_in[j], p.M, o_new));
-                                if (MODE == DBOT_MODE_UPDATE) __stcs(occ_out + u.g + 32 * j, o_new);
+                                if (MODE == DBOT_MODE_UPDATE)
+                                    __stcs(occ_out + u.g + 32 * j, dbot_mul(dbot_sub(o_new, p.post_b), p.post_inv_a));
                             }
                     };
 #ifdef DBOT_DBG_NO_PIXELS
@@ -763,11 +923,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                 }
             }
         }
-        if (MODE == DBOT_MODE_UPDATE && !copied)
-        {
-            role_sync(DBOT_BAR_COPIED);
-            role_arrive(DBOT_BAR_CONSUMED);
-        }
+        if (MODE == DBOT_MODE_UPDATE && !copied) await_slot();
 
         /* ---- one log-weight per particle: fixed shuffle tree, double across warps ---- */
         if (MODE != DBOT_MODE_RENDER)
@@ -783,7 +939,15 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
 #pragma unroll
                 for (int w = 0; w < DBOT_CW; ++w) s += s_red[w];
                 p.out[i] = s;
-                if (MODE == DBOT_MODE_UPDATE) p.indices[i] = i;
+                if (MODE == DBOT_MODE_UPDATE)
+                {
+                    p.indices[i] = i;
+                    if (pl.x != pl.y) /* done with the parent's slot: its adopter may write into it */
+                    {
+                        __threadfence();
+                        atomicSub(p.pending + pl.z, 1);
+                    }
+                }
             }
         }
     }
@@ -827,7 +991,12 @@ struct dbot_b200_sensor
     dbot_chunk* d_chunks;
     float* d_obs;
     float4* d_tab;
-    float* d_occ[2];
+    float* d_pool;          /* 2 * max_particles physical occlusion slots */
+    int32_t* d_loc[2];      /* logical -> physical slot, current / next generation */
+    int32_t* d_free;        /* stack of unused physical slots + its height */
+    int32_t* d_free_count;
+    int32_t *d_cnt, *d_last, *d_pending, *d_order;
+    int4* d_plan;
     float* d_poses;
     int32_t* d_indices;
     double* d_out;
@@ -841,8 +1010,15 @@ struct dbot_b200_sensor
     float* h_depth;
     int* h_err;
     /* state */
-    int cur, n_slots;
+    int cur, n_slots;       /* cur: which d_loc is current */
     double t_obs, t_update;
+    /* lazy propagation: a stored value r of any slot stands for the occlusion probability
+     * A * r + B as of t_update.  dbot's OcclusionModel propagates by an affine map that is the same
+     * for every pixel of every slot, so the maps of successive updates compose into these two
+     * numbers (kept in double) instead of being applied to 4*P bytes per particle per frame; an
+     * update copies stored values verbatim and encodes the posterior of the covered pixels as
+     * (o - B) / A.  Equivalent to the eager propagation of dbot's GPU evaluator. */
+    double A, B;
     /* measurement */
     cudaEvent_t ev_begin, ev_end, ev_k0, ev_k1, ev_obs;
     int obs_in_flight; /* the staged depth frame may still be on its way to the device */
@@ -940,7 +1116,9 @@ extern "C" int dbot_b200_destroy(dbot_b200_sensor* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_mesh); cudaFree(s->d_chunks); cudaFree(s->d_obs); cudaFree(s->d_tab);
-    cudaFree(s->d_occ[0]); cudaFree(s->d_occ[1]); cudaFree(s->d_poses); cudaFree(s->d_indices);
+    cudaFree(s->d_pool); cudaFree(s->d_loc[0]); cudaFree(s->d_loc[1]); cudaFree(s->d_free);
+    cudaFree(s->d_free_count); cudaFree(s->d_cnt); cudaFree(s->d_last); cudaFree(s->d_pending);
+    cudaFree(s->d_order); cudaFree(s->d_plan); cudaFree(s->d_poses); cudaFree(s->d_indices);
     cudaFree(s->d_out); cudaFree(s->d_depth); cudaFree(s->d_err);
     cudaFreeHost(s->h_poses); cudaFreeHost(s->h_indices); cudaFreeHost(s->h_out);
     cudaFreeHost(s->h_obs); cudaFreeHost(s->h_depth); cudaFreeHost(s->h_err);
@@ -1047,8 +1225,16 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     const size_t state_bytes = np * kp.slot_stride * sizeof(float);
     CUDA_TRY(cudaMalloc(&s->d_obs, P * sizeof(float)));
     CUDA_TRY(cudaMalloc(&s->d_tab, kp.slot_stride * sizeof(float4)));
-    CUDA_TRY(cudaMalloc(&s->d_occ[0], state_bytes));
-    CUDA_TRY(cudaMalloc(&s->d_occ[1], state_bytes));
+    CUDA_TRY(cudaMalloc(&s->d_pool, 2 * state_bytes));
+    CUDA_TRY(cudaMalloc(&s->d_loc[0], np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_loc[1], np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_free, 2 * np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_free_count, sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_cnt, np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_last, np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_pending, np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_order, np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_plan, np * sizeof(int4)));
     CUDA_TRY(cudaMalloc(&s->d_poses, np * 12 * kp.n_obj * sizeof(float)));
     CUDA_TRY(cudaMalloc(&s->d_indices, np * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&s->d_out, np * sizeof(double)));
@@ -1056,7 +1242,7 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     CUDA_TRY(cudaMalloc(&s->d_err, sizeof(int)));
     CUDA_TRY(cudaMemset(s->d_err, 0, sizeof(int)));
     s->device_bytes += (int64_t)(2 * P * sizeof(float) + kp.slot_stride * sizeof(float4) +
-                                 2 * state_bytes + np * (12 * kp.n_obj * 4 + 4 + 8) + 4);
+                                 2 * state_bytes + np * (12 * kp.n_obj * 4 + 4 + 8 + 8 * 4 + 16) + 8);
     CUDA_TRY(cudaHostAlloc(&s->h_poses, np * 12 * kp.n_obj * sizeof(float), cudaHostAllocDefault));
     CUDA_TRY(cudaHostAlloc(&s->h_indices, np * sizeof(int32_t), cudaHostAllocDefault));
     CUDA_TRY(cudaHostAlloc(&s->h_out, np * sizeof(double), cudaHostAllocDefault));
@@ -1120,7 +1306,19 @@ static void prof_end(dbot_b200_sensor* s, int which)
     s->prof_launches[which]++;
 }
 
-/* RbSensor::reset */
+/* RbSensor::reset: one logical slot (physical slot 0) at initial_occlusion_prob,
+ * every other physical slot free */
+__global__ void dbot_reset_slots_kernel(int32_t* loc, int32_t* free_stack, int32_t* free_count, int n_phys)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0)
+    {
+        loc[0] = 0;
+        *free_count = n_phys - 1;
+    }
+    if (i < n_phys - 1) free_stack[i] = n_phys - 1 - i; /* top of the stack = slot 1 */
+}
+
 extern "C" int dbot_b200_reset(dbot_b200_sensor* s)
 {
     if (!s) return fail(-1, "reset: null handle");
@@ -1129,9 +1327,14 @@ extern "C" int dbot_b200_reset(dbot_b200_sensor* s)
     s->n_slots = 1;
     s->t_obs = 0.0;
     s->t_update = 0.0;
-    dbot_fill_kernel<<<64, 256, 0, s->stream>>>(s->d_occ[0], s->kp.slot_stride,
+    s->A = 1.0;
+    s->B = 0.0;
+    const int n_phys = 2 * s->cfg.max_particles;
+    dbot_fill_kernel<<<64, 256, 0, s->stream>>>(s->d_pool, s->kp.slot_stride,
                                                 (float)s->cfg.initial_occlusion_prob);
-    s->launches++;
+    dbot_reset_slots_kernel<<<(n_phys + 255) / 256, 256, 0, s->stream>>>(s->d_loc[0], s->d_free,
+                                                                         s->d_free_count, n_phys);
+    s->launches += 2;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return 0;
@@ -1195,33 +1398,75 @@ extern "C" int dbot_b200_set_observation_device(dbot_b200_sensor* s, const float
     return launch_observation(s, d_depth_m);
 }
 
-/* occlusion propagation over dt as an affine map (dbot OcclusionModel) */
-static void propagation_affine(const dbot_b200_sensor* s, double dt, float* a, float* b)
+/* occlusion propagation over dt as an affine map o -> a o + b (dbot OcclusionModel) */
+static void propagation_affine(const dbot_b200_sensor* s, double dt, double* a, double* b)
 {
     const double ct = exp(dt * s->log_c);
     const double k = (1.0 - s->cfg.p_occluded_occluded) * (ct - 1.0) / (s->c - 1.0);
-    *a = (float)ct;
-    *b = (float)(1.0 - ct - k);
+    *a = ct;
+    *b = 1.0 - ct - k;
 }
+/* stored value -> occlusion probability as of the current observation time */
+static void state_affine_now(const dbot_b200_sensor* s, double* A, double* B)
+{
+    double a, b;
+    propagation_affine(s, s->t_obs - s->t_update, &a, &b);
+    *A = a * s->A;
+    *B = a * s->B + b;
+}
+
+#define DBOT_REBASE_BELOW 8.673617379884035e-19 /* 2^-60 */
 
 static int launch_particles(dbot_b200_sensor* s, const float* d_poses, int32_t* d_indices, int n,
                             int update, double* d_out)
 {
+    double A, B;
+    state_affine_now(s, &A, &B);
+    if (update && A < DBOT_REBASE_BELOW)
+    {
+        /* fold the accumulated map into the stored values before it leaves float range */
+        dbot_rebase_kernel<<<dim3(32, std::min(s->n_slots, 4096)), 256, 0, s->stream>>>(
+            s->d_pool, s->d_loc[s->cur], s->n_slots, s->kp.slot_stride, (float)s->A, (float)s->B);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        s->A = 1.0;
+        s->B = 0.0;
+        state_affine_now(s, &A, &B);
+    }
     dbot_kparams kp = s->kp;
     kp.n = n;
     kp.n_slots = s->n_slots;
     kp.tab = s->d_tab;
-    kp.occ_in = s->d_occ[s->cur];
-    kp.occ_out = s->d_occ[s->cur ^ 1];
+    kp.pool = s->d_pool;
+    kp.loc = s->d_loc[s->cur];
+    kp.plan = s->d_plan;
+    kp.order = s->d_order;
+    kp.pending = s->d_pending;
     kp.poses = d_poses;
     kp.indices = d_indices;
     kp.out = d_out;
     kp.err_flag = s->d_err;
-    propagation_affine(s, s->t_obs - s->t_update, &kp.M.prop_a, &kp.M.prop_b);
+    kp.M.prop_a = (float)A;
+    kp.M.prop_b = (float)B;
+    kp.post_b = (float)B;
+    kp.post_inv_a = (float)(1.0 / A);
+    if (update)
+    {
+        dbot_plan_update_kernel<<<1, DBOT_PLAN_THREADS, 0, s->stream>>>(
+            d_indices, n, s->n_slots, s->d_loc[s->cur], s->d_loc[s->cur ^ 1], s->d_free, s->d_free_count,
+            s->d_cnt, s->d_last, s->d_pending, s->d_order, s->d_plan, s->d_err);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
     const int grid = std::min(n, s->grid_max);
     prof_begin(s);
     if (update)
-        dbot_particle_kernel<DBOT_MODE_UPDATE><<<grid, DBOT_CT + DBOT_ST, s->smem_bytes, s->stream>>>(kp);
+    {
+        /* adopting children spin on their siblings' copies: every CTA must be resident */
+        void* args[] = {(void*)&kp};
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)dbot_particle_kernel<DBOT_MODE_UPDATE>, dim3(grid),
+                                             dim3(DBOT_CT + DBOT_ST), args, (size_t)s->smem_bytes, s->stream));
+    }
     else
         dbot_particle_kernel<DBOT_MODE_EVAL><<<grid, DBOT_CT, s->smem_bytes, s->stream>>>(kp);
     CUDA_TRY(cudaGetLastError());
@@ -1231,6 +1476,8 @@ static int launch_particles(dbot_b200_sensor* s, const float* d_poses, int32_t* 
         s->cur ^= 1;
         s->n_slots = n;
         s->t_update = s->t_obs;
+        s->A = A;
+        s->B = B;
     }
     return 0;
 }
@@ -1339,13 +1586,15 @@ extern "C" int dbot_b200_get_occlusion(dbot_b200_sensor* s, int32_t slot, float*
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     const int rows = s->kp.rows, cols = s->kp.cols, pitch = s->kp.pitch;
     std::vector<float> tmp((size_t)rows * cols);
+    int32_t phys = 0;
+    CUDA_TRY(cudaMemcpy(&phys, s->d_loc[s->cur] + slot, sizeof(int32_t), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy2D(tmp.data(), (size_t)cols * sizeof(float),
-                          s->d_occ[s->cur] + (size_t)slot * s->kp.slot_stride,
+                          s->d_pool + (size_t)phys * s->kp.slot_stride,
                           (size_t)pitch * sizeof(float), (size_t)cols * sizeof(float), rows,
                           cudaMemcpyDeviceToHost));
-    float a, b;
-    propagation_affine(s, s->t_obs - s->t_update, &a, &b);
-    for (size_t i = 0; i < tmp.size(); ++i) out_occ[i] = fmaf(a, tmp[i], b);
+    double A, B;
+    state_affine_now(s, &A, &B);
+    for (size_t i = 0; i < tmp.size(); ++i) out_occ[i] = fmaf((float)A, tmp[i], (float)B);
     return 0;
 }
 

@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--parents", default="resampled", choices=["resampled", "identity"],
+                    help="parent pattern of the update calls: systematic resampling every frame, or none")
     a = ap.parse_args()
     import torch
 
@@ -36,7 +38,8 @@ def main():
     gt = synth.ground_truth_poses(len(w["V"]), rng)
     frames = [synth.make_frame(sensor.render, gt, rows, cols, rng) for _ in range(2)]
     poses = [synth.particle_poses(gt, n, rng) for _ in range(2)]
-    parents = [bench.resampled_parents(n, rng) for _ in range(2)]
+    parents = [bench.resampled_parents(n, rng) if a.parents == "resampled" else np.arange(n, dtype=np.int32)
+               for _ in range(2)]
     dev = torch.device("cuda", 0)
     d_frames = [torch.from_numpy(f).to(dev) for f in frames]
     d_poses = [torch.from_numpy(p).to(dev) for p in poses]
@@ -60,7 +63,7 @@ def main():
         sensor.synchronize()
     prof = sensor.profile_read()
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-    out = {"config": a.config, "n": n, "resolution": [cols, rows], "triangles": w["tris"],
+    out = {"config": a.config, "n": n, "parents": a.parents, "resolution": [cols, rows], "triangles": w["tris"],
            "device_bytes": sensor.device_bytes}
     for mode, bytes_per in (("loglikes", None), ("update", 8.0 * P)):
         ms, cnt = prof[mode]
