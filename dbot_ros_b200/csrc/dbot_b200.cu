@@ -1578,6 +1578,15 @@ extern "C" int dbot_b200_render(dbot_b200_sensor* s, const float* pose, float* o
 extern "C" int dbot_b200_n_slots(dbot_b200_sensor* s) { return s ? s->n_slots : -1; }
 extern "C" double dbot_b200_observation_time(dbot_b200_sensor* s) { return s ? s->t_obs : NAN; }
 
+extern "C" int dbot_b200_free_slot_count(dbot_b200_sensor* s)
+{
+    if (!s) return -1;
+    if (cudaSetDevice(s->device) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess) return -1;
+    int32_t f = -1;
+    if (cudaMemcpy(&f, s->d_free_count, sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return f;
+}
+
 extern "C" int dbot_b200_get_occlusion(dbot_b200_sensor* s, int32_t slot, float* out_occ)
 {
     if (!s || !out_occ) return fail(-1, "get_occlusion: null argument");

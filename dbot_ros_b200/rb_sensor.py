@@ -299,6 +299,10 @@ class B200KinectImageModel(RbSensor):
         return self._lib.dbot_b200_n_slots(self._h)
 
     @property
+    def free_slots(self):
+        return self._lib.dbot_b200_free_slot_count(self._h)
+
+    @property
     def observation_time(self):
         return self._lib.dbot_b200_observation_time(self._h)
 

@@ -57,9 +57,9 @@ typedef struct
         initial_occlusion_prob;                    /* ref:config/particle_tracker.yaml:41-43 */
     double delta_time;   /* ref:source/dbot_ros/tracker/particle_tracker_node.cpp:189 (1/30) */
     int32_t device_id;   /* CUDA device ordinal of this handle (one handle per GPU) */
-    int32_t occlusion_mode; /* 0 = dense eager: one full-frame fp32 occlusion image per
-                               particle, propagated on every update (semantics of dbot's GPU
-                               evaluator).  Other values are reserved. */
+    int32_t occlusion_mode; /* 0 = dense: one full-frame fp32 occlusion image per particle with the
+                               semantics of dbot's GPU evaluator (whole image propagated on every
+                               update).  Other values are reserved. */
 } dbot_b200_config;
 
 /* RbSensorBuilder<State>::build() with use_gpu == true */
@@ -98,6 +98,8 @@ int dbot_b200_synchronize(dbot_b200_sensor* s);
 /* ---- state read-back (tests, debugging) ---- */
 int dbot_b200_n_slots(dbot_b200_sensor* s);
 double dbot_b200_observation_time(dbot_b200_sensor* s);
+/* physical occlusion slots not in use (pool of 2*max_particles; n_slots + free == pool size) */
+int dbot_b200_free_slot_count(dbot_b200_sensor* s);
 /* occlusion probability image of one slot as of the current observation time, rows*cols floats */
 int dbot_b200_get_occlusion(dbot_b200_sensor* s, int32_t slot, float* out_occ);
 

@@ -287,3 +287,69 @@ def test_observation_paths_pinned_and_staged():
     orc.set_observation(f2)
     assert rel_err(sensor.loglikes_poses(poses, np.zeros(n, np.int32), False),
                    orc.loglikes_poses(poses, np.zeros(n, np.int32), False)) < REL_TOL
+
+
+def test_slot_adoption_patterns_and_pool_accounting():
+    """The update plan (last child adopts the parent's slot, the others copy into free slots) must
+    be invisible: identity parents, one parent for everybody, shrinking and growing particle sets,
+    repeated and unused parents -- log-weights and occlusion images track the oracle, and no
+    physical slot is ever lost (free + live == pool)."""
+    cap = 48
+    sensor, orc, rows, cols, n_obj = make_pair("ico80", 8, cap)
+    rng = np.random.default_rng(21)
+    gt = synth.ground_truth_poses(n_obj, rng)
+    n_prev = 1
+    schedule = [("same", 32), ("identity", 32), ("identity", 32), ("random", 32), ("shrink", 7),
+                ("random", 48), ("reverse", 48), ("half", 48), ("identity", 48), ("same", 5)]
+    for f, (kind, n) in enumerate(schedule):
+        frame = synth.make_frame(orc.render, gt, rows, cols, rng)
+        poses = synth.particle_poses(gt, n, rng, sigma_t=0.01, sigma_r=0.1)
+        if kind == "same":
+            par = np.full(n, rng.integers(0, n_prev), dtype=np.int32)
+        elif kind == "identity":
+            par = np.arange(n, dtype=np.int32)
+        elif kind == "reverse":
+            par = np.arange(n, dtype=np.int32)[::-1].copy()
+        elif kind == "half":
+            par = (np.arange(n, dtype=np.int32) // 2) * 2
+        else:
+            par = rng.integers(0, n_prev, size=n).astype(np.int32)
+        ia, ib = par.copy(), par.copy()
+        sensor.set_observation(frame)
+        orc.set_observation(frame)
+        got = sensor.loglikes_poses(poses, ia, True)
+        want = orc.loglikes_poses(poses, ib, True)
+        assert rel_err(got, want) < REL_TOL, (f, kind)
+        assert sensor.n_slots == n and sensor.free_slots + n == 2 * cap, (f, kind)
+        for slot in {0, n // 2, n - 1}:
+            assert np.max(np.abs(sensor.occlusion(slot) - orc.occlusion(slot))) < 2 * OCC_TOL, (f, kind, slot)
+        n_prev = n
+    sensor.reset()
+    assert sensor.n_slots == 1 and sensor.free_slots == 2 * cap - 1
+
+
+def test_lazy_propagation_rebase():
+    """With 5 s between frames the composed propagation factor falls below 2^-60 after 17 updates
+    and the stored values are rebased; the read-back and the log-weights must not notice."""
+    n = 12
+    rows, cols = synth.resolution(8)
+    K = synth.camera_matrix(8)
+    V, T = synth.mesh_set("ico80")
+    prm = dict(synth.default_parameters(), delta_time=5.0)
+    sensor = RbSensorBuilder(ObjectModel(V, T), CameraData(K, rows, cols),
+                             Parameters(sample_count=n, delta_time=5.0)).build()
+    orc = oracle_lib.Oracle(rows, cols, K, V, T, prm)
+    rng = np.random.default_rng(33)
+    gt = synth.ground_truth_poses(1, rng)
+    idx = np.zeros(n, dtype=np.int32)
+    for f in range(40):
+        frame = synth.make_frame(orc.render, gt, rows, cols, rng)
+        poses = synth.particle_poses(gt, n, rng, sigma_t=0.01, sigma_r=0.1)
+        par = idx.copy() if f == 0 else rng.integers(0, n, size=n).astype(np.int32)
+        ia, ib = par.copy(), par.copy()
+        sensor.set_observation(frame)
+        orc.set_observation(frame)
+        got = sensor.loglikes_poses(poses, ia, True)
+        want = orc.loglikes_poses(poses, ib, True)
+        assert rel_err(got, want) < REL_TOL, f
+        assert np.max(np.abs(sensor.occlusion(n - 1) - orc.occlusion(n - 1))) < 2 * OCC_TOL, f
