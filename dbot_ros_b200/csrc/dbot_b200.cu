@@ -48,9 +48,6 @@
 #define DBOT_CHUNK_MAX_VERTS 3072
 #define DBOT_CHUNK_MAX_TRIS 6144
 #define DBOT_FULL 0xffffffffu
-#ifndef DBOT_RASTER_VARIANT
-#define DBOT_RASTER_VARIANT 0
-#endif
 #ifndef DBOT_UNIT_PX
 #define DBOT_UNIT_PX 4             /* pixels per lane and unit of the mixture pass */
 #endif
@@ -354,9 +351,8 @@ __global__ void __launch_bounds__(DBOT_PLAN_THREADS, 1)
  * blocks of 8 columns x 4 rows and the blocks are dealt out evenly over the lanes (prefix sum
  * over the block counts, owner table in shared memory, owner's parameters by shuffle), so every
  * lane always has a block to work on however unequal the triangles are.  A block is processed
- * row by row without branches on coverage: 8 x (three int32 edge functions, sign test, one fma
- * for the inverse depth, predicated read of the tile), then 8 x (compare, shared-memory max on
- * the bits of the positive float for the fragments that win).
+ * row by row without any branch: 8 x (three int32 edge functions, sign test, one fma for the
+ * inverse depth, address select, shared-memory max on the bits of the positive float).
  * Pixels of a block outside the triangle's own box fail the edge test by themselves, so no
  * box mask is needed -- unless the box was cut by the raster window; those triangles, the ones
  * that need int64 edge functions and the ones whose box dwarfs the batch are instead walked by
@@ -367,34 +363,6 @@ __device__ __forceinline__ void dbot_zmax(uint32_t* p, uint32_t v)
 {
     if (v > *p) atomicMax(p, v); /* plain read first: fragments that lose the test cost no atomic */
 }
-/* predicated tile read: the current inverse depth where the pixel is covered, else "infinitely
- * near" so that the fragment loses */
-__device__ __forceinline__ uint32_t dbot_tile_read_if(uint32_t tile_addr, int edge_or)
-{
-    uint32_t cur = 0xffffffffu;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ge.s32 p, %1, 0;\n"
-        "@p ld.shared.u32 %0, [%2];\n"
-        "}"
-        : "+r"(cur)
-        : "r"(edge_or), "r"(tile_addr)
-        : "memory");
-    return cur;
-}
-__device__ __forceinline__ void dbot_tile_max_if(uint32_t tile_addr, uint32_t bits, uint32_t cur)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred q;\n"
-        "setp.gt.u32 q, %1, %2;\n"
-        "@q red.shared.max.u32 [%0], %1;\n"
-        "}" ::"r"(tile_addr),
-        "r"(bits), "r"(cur)
-        : "memory");
-}
-
 __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s_tri, int ntri,
                                                   const float4* __restrict__ s_v4,
                                                   const int* __restrict__ s_Y, const dbot_camera& K,
@@ -403,6 +371,8 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
 {
     const int ww = col1 - col0 + 1;
     const uint32_t tile_s = smem_u32(s_wt);
+    __shared__ uint32_t s_dummy[DBOT_CW][32];
+    const uint32_t dummy_s = smem_u32(&s_dummy[threadIdx.x >> 5][lane]);
     for (;;)
     {
         int base = 0;
@@ -510,42 +480,19 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
             for (int rr = 0; rr < 4; ++rr)
             {
                 const float wr = dbot_fmaf(o_m1, fr, o_m2);
-                uint32_t bits[8], cur[8];
-#if DBOT_RASTER_VARIANT == 0
+                /* Branch-free resolve.  ptxas wraps every predicated shared-memory atomic in a
+                 * BSSY/BRA/BSYNC triple, and a read-compare-branch in front of it costs more issue
+                 * slots than the atomics it saves; so every covered pixel sends its inverse depth
+                 * to the tile's max, and every pixel outside the triangle sends it to a per-lane
+                 * dummy word instead (own bank: no conflict, no branch). */
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc)
                 {
                     const int eor = (x0 + cc * o_e0c) | (x1 + cc * o_e1c) | (x2 + cc * o_e2c);
-                    bits[cc] = dbot_f2u(fminf(fmaxf(dbot_fmaf(o_m0, fc[cc], wr), o_wlo), o_whi));
-                    cur[cc] = dbot_tile_read_if(trow + 4u * cc, eor);
+                    const uint32_t bits = dbot_f2u(fminf(fmaxf(dbot_fmaf(o_m0, fc[cc], wr), o_wlo), o_whi));
+                    const uint32_t a = eor >= 0 ? trow + 4u * cc : dummy_s;
+                    asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(a), "r"(bits) : "memory");
                 }
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) dbot_tile_max_if(trow + 4u * cc, bits[cc], cur[cc]);
-#elif DBOT_RASTER_VARIANT == 1
-                uint32_t* prow = s_wt + ((trow - tile_s) >> 2);
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc)
-                {
-                    const int eor = (x0 + cc * o_e0c) | (x1 + cc * o_e1c) | (x2 + cc * o_e2c);
-                    bits[cc] = dbot_f2u(fminf(fmaxf(dbot_fmaf(o_m0, fc[cc], wr), o_wlo), o_whi));
-                    cur[cc] = eor >= 0 ? prow[cc] : 0xffffffffu;
-                }
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc)
-                    if (bits[cc] > cur[cc]) atomicMax(prow + cc, bits[cc]);
-#else
-                uint32_t* prow = s_wt + ((trow - tile_s) >> 2);
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc)
-                {
-                    const int eor = (x0 + cc * o_e0c) | (x1 + cc * o_e1c) | (x2 + cc * o_e2c);
-                    bits[cc] = dbot_f2u(fminf(fmaxf(dbot_fmaf(o_m0, fc[cc], wr), o_wlo), o_whi));
-                    cur[cc] = (uint32_t)eor;
-                }
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc)
-                    if ((int)cur[cc] >= 0) atomicMax(prow + cc, bits[cc]);
-#endif
                 x0 += o_e0r; x1 += o_e1r; x2 += o_e2r;
                 fr = dbot_add(fr, 1.0f);
                 trow += 4u * (uint32_t)ww;
@@ -1206,7 +1153,8 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     kp.off_v4 = off;  off += round_up((uint32_t)max_nv * 16u, 128);
     kp.off_Y = off;   off += round_up((uint32_t)max_nv * 4u, 128);
     kp.off_wt = off;
-    const int smem_max = (int)prop.sharedMemPerBlockOptin - 1024 - DBOT_CW * DBOT_OWNER_CAP; /* static __shared__ + slack */
+    /* static __shared__ (owner tables, dummy words, hand-off) + slack */
+    const int smem_max = (int)prop.sharedMemPerBlockOptin - 1024 - DBOT_CW * DBOT_OWNER_CAP - DBOT_CW * 128;
     if ((int)off + 4 * (int)round_up((uint32_t)kp.cols, 4) > smem_max)
         return fail(-9, "image too wide for the shared-memory depth tile (cols=%d)", kp.cols);
     s->smem_bytes = smem_max;
