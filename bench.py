@@ -271,8 +271,11 @@ def main():
     sensor.loglikes_poses(poses[0], np.zeros(n, dtype=np.int32), True)
     timed(device_step, args.warmup)
     launches0 = sensor.launch_count
-    with ClockSampler(local_rank) as clocks:
-        ms = timed(device_step, args.steps)
+    # clocks are sampled from here to the end of the three timed loops (device-resident, end-to-end,
+    # per-kernel); a few tens of milliseconds of GPU work are too short for one loop alone
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
+    ms = timed(device_step, args.steps)
     gpu_launches = int(sensor.launch_count - launches0)
     value = n * world * args.steps / (ms * 1e-3)
 
@@ -333,6 +336,7 @@ def main():
     sync_all()
     prof = sensor.profile_read()
     sensor.profile_enable(False)
+    clocks.__exit__()
     k_ms, k_cnt = prof["update"]
     o_ms, o_cnt = prof["observation"]
     peaks = {}
