@@ -346,13 +346,21 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:  # one ncu --set full capture of the same kernel and workload, committed under profiles/
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
     alg_bytes = 8.0 * P * n                       # 4P read + 4P written per particle
     avg_ms = k_ms / max(k_cnt, 1)
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "dbot_particle_kernel<UPDATE>", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu dram__bytes_read.sum + "
+                "dram__bytes_write.sum, one launch)" if traffic else None,
+                "algorithmic_bytes_per_launch": alg_bytes,
                 "avg_launch_ms": avg_ms, "launches_timed": k_cnt,
                 "kernel_share_of_step": k_ms / max(k_ms + o_ms, 1e-9),
                 "observation_kernel_avg_ms": o_ms / max(o_cnt, 1)}

@@ -851,7 +851,10 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                             if (u.wb[j] != DBOT_W_EMPTY && u.tab[j].x == u.tab[j].x)
                             {
                                 float o_new;
-                                acc = dbot_add(acc, dbot_pixel_term(dbot_rcp_fast(dbot_u2f(u.wb[j])), u.tab[j],
+                                /* the correctly rounded reciprocal, not MUFU alone: the oracle's
+                                 * (and dbot's) predicted depth is the float the renderer stores, and
+                                 * d - y cancels -- one ulp of d is 1e-5 in the Gaussian's argument */
+                                acc = dbot_add(acc, dbot_pixel_term(dbot_rcp(dbot_u2f(u.wb[j])), u.tab[j],
                                                                     u.o_in[j], p.M, o_new));
                                 if (MODE == DBOT_MODE_UPDATE)
                                     __stcs(occ_out + u.g + 32 * j, dbot_mul(dbot_sub(o_new, p.post_b), p.post_inv_a));
