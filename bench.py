@@ -219,6 +219,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device (dbot_ros_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     w = workload()
