@@ -194,7 +194,28 @@ def run_reference(args):
                              "why_port": "the reference's evaluator lives in the un-vendored dbot library "
                                          "(needs Eigen 3.2, fl, catkin): not buildable here, see DESIGN.md"},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL prints its
+    version banner there) is sent to stderr, and emit() writes the line to the real stdout"""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -206,6 +227,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -219,9 +241,6 @@ def main():
         raise SystemExit("bench.py: no CUDA device (dbot_ros_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     w = workload()
@@ -383,7 +402,7 @@ def main():
                                 "sample": "%d of the %d particles per step, %d steps (%.1f s of CPU work), same "
                                           "frames, OpenMP over particles" % (sample, n, reps, sec * reps)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
