@@ -108,6 +108,14 @@ def test_argument_errors_need_no_device():
     bad = dict(kw, p_occluded_occluded=0.1)
     cfg, keep = abi.make_config(60, 80, synth.camera_matrix(8), 4, V, T, **bad)
     assert lib.dbot_b200_create(C.byref(cfg), C.byref(h)) == -4       # c = p_oo - p_ov must be in (0,1)
+    many = synth.mesh_set("ico80")
+    cfg, keep = abi.make_config(60, 80, synth.camera_matrix(8), 4, many[0] * 9, many[1] * 9, **kw)
+    assert lib.dbot_b200_create(C.byref(cfg), C.byref(h)) == -2       # more than DBOT_B200_MAX_OBJECTS
+    cfg, keep = abi.make_config(60, 80, synth.camera_matrix(8), 0, V, T, **kw)
+    assert lib.dbot_b200_create(C.byref(cfg), C.byref(h)) == -2       # max_particles must be positive
+    cfg, keep = abi.make_config(60, 80, synth.camera_matrix(8), 4, V, T, **dict(kw), occlusion_mode=1)
+    assert lib.dbot_b200_create(C.byref(cfg), C.byref(h)) == -2       # reserved mode
+    assert h.value is None
     assert lib.dbot_b200_reset(None) == -1
     assert lib.dbot_b200_loglikes(None, None, None, 0, 0, None) == -1
     assert lib.dbot_b200_n_slots(None) == -1

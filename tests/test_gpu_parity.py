@@ -353,3 +353,45 @@ def test_lazy_propagation_rebase():
         want = orc.loglikes_poses(poses, ib, True)
         assert rel_err(got, want) < REL_TOL, f
         assert np.max(np.abs(sensor.occlusion(n - 1) - orc.occlusion(n - 1))) < 2 * OCC_TOL, f
+
+
+def test_maximum_sizes_and_ragged_inputs():
+    """Edges of the configuration space: the maximum number of objects (8) with ragged mesh sizes
+    including an object without triangles; a 1280x960 frame with the object close enough that the
+    window needs several z-tile bands; a single particle."""
+    rng = np.random.default_rng(17)
+    # -- 8 objects, ragged meshes, one of them empty ------------------------------------------
+    parts = [synth.icosphere(1, radius=0.03, seed=k) for k in range(6)]
+    parts.append(synth.uv_ellipsoid(6, 7, radii=(0.03, 0.02, 0.02)))
+    parts.append((np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32)))
+    V, T = [p[0] for p in parts], [p[1] for p in parts]
+    sensor, orc, rows, cols, n_obj = make_pair((V, T), 4, 6)
+    assert n_obj == 8
+    gt = [(synth.rodrigues(rng.normal(size=3)), np.array([-0.21 + 0.06 * o, 0.02 * (o % 3 - 1), 0.7 + 0.03 * o]))
+          for o in range(8)]
+    frame = synth.make_frame(orc.render, gt, rows, cols, rng)
+    poses = synth.particle_poses(gt, 6, rng)
+    for s in (sensor, orc):
+        s.set_observation(frame)
+    ia, ib = np.zeros(6, np.int32), np.zeros(6, np.int32)
+    assert np.array_equal(sensor.render(poses[0]).view(np.uint32), orc.render(poses[0]).view(np.uint32))
+    assert rel_err(sensor.loglikes_poses(poses, ia, True), orc.loglikes_poses(poses, ib, True)) < REL_TOL
+    assert np.max(np.abs(sensor.occlusion(5) - orc.occlusion(5))) < OCC_TOL
+    # -- 1280 x 960, window far larger than the z tile -----------------------------------------
+    rows, cols = 960, 1280
+    K = np.array([[1160.0, 0.0, 640.0], [0.0, 1160.0, 480.0], [0.0, 0.0, 1.0]])
+    Vb, Tb = synth.mesh_set("icosphere5k")
+    sensor = RbSensorBuilder(ObjectModel(Vb, Tb), CameraData(K, rows, cols), Parameters(sample_count=2)).build()
+    orc = oracle_lib.Oracle(rows, cols, K, Vb, Tb, synth.default_parameters())
+    gt = [(synth.rodrigues([0.2, 0.1, -0.3]), np.array([0.01, -0.02, 0.4]))]
+    pose = synth.pack_pose(*gt[0])
+    want = orc.render(pose)
+    assert np.isfinite(want).sum() > 200000          # > 5 bands of the shared-memory tile
+    assert np.array_equal(sensor.render(pose).view(np.uint32), want.view(np.uint32))
+    frame = synth.make_frame(orc.render, gt, rows, cols, rng)
+    poses = synth.particle_poses(gt, 1, rng)         # a single particle
+    for s in (sensor, orc):
+        s.set_observation(frame)
+    ia, ib = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    assert rel_err(sensor.loglikes_poses(poses, ia, True), orc.loglikes_poses(poses, ib, True)) < REL_TOL
+    assert np.max(np.abs(sensor.occlusion(0) - orc.occlusion(0))) < OCC_TOL
