@@ -59,6 +59,9 @@ SIGNATURES = {
     "dbot_b200_loglikes_device": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
     "dbot_b200_stream": (_P, [_P]),
     "dbot_b200_synchronize": (C.c_int, [_P]),
+    "dbot_b200_slot_floats": (C.c_int64, [_P]),
+    "dbot_b200_export_slot_device": (C.c_int, [_P, C.c_int32, _P]),
+    "dbot_b200_import_slot_device": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
     "dbot_b200_n_slots": (C.c_int, [_P]),
     "dbot_b200_observation_time": (C.c_double, [_P]),
     "dbot_b200_free_slot_count": (C.c_int, [_P]),

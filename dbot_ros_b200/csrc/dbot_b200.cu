@@ -306,6 +306,18 @@ __global__ void __launch_bounds__(DBOT_PLAN_THREADS, 1)
     int crank = dbot_block_exclusive_scan(copies, s_warp, &n_copies);
     int arank = dbot_block_exclusive_scan(adopts, s_warp, &n_adopts);
     const int f0 = *free_count;
+    if (f0 < n_copies)
+    {
+        /* cannot happen while live + imported slots <= pool / 2 (see dbot_b200_import_slot) */
+        if (t == 0) atomicExch(err_flag, 2);
+        for (int i = i0; i < i1; ++i)
+        {
+            plan[i] = make_int4(-1, 0, 0, 0);
+            order[i] = i;
+            loc_next[i] = loc[0];
+        }
+        return;
+    }
     for (int i = i0; i < i1; ++i)
     {
         const int par = parents[i];
@@ -1177,13 +1189,13 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     CUDA_TRY(cudaMalloc(&s->d_obs, P * sizeof(float)));
     CUDA_TRY(cudaMalloc(&s->d_tab, kp.slot_stride * sizeof(float4)));
     CUDA_TRY(cudaMalloc(&s->d_pool, 2 * state_bytes));
-    CUDA_TRY(cudaMalloc(&s->d_loc[0], np * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&s->d_loc[1], np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_loc[0], 2 * np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_loc[1], 2 * np * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&s->d_free, 2 * np * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&s->d_free_count, sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&s->d_cnt, np * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&s->d_last, np * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&s->d_pending, np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_cnt, 2 * np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_last, 2 * np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_pending, 2 * np * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&s->d_order, np * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&s->d_plan, np * sizeof(int4)));
     CUDA_TRY(cudaMalloc(&s->d_poses, np * 12 * kp.n_obj * sizeof(float)));
@@ -1485,7 +1497,9 @@ extern "C" int dbot_b200_synchronize(dbot_b200_sensor* s)
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (*s->h_err)
     {
+        const int code = *s->h_err;
         cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream);
+        if (code == 2) return fail(-10, "the occlusion-slot pool is exhausted (too many imported slots)");
         return fail(-7, "loglikes_device: an index was not a valid occlusion slot");
     }
     return 0;
@@ -1528,6 +1542,70 @@ extern "C" int dbot_b200_render(dbot_b200_sensor* s, const float* pose, float* o
 /* ---- state read-back ---- */
 extern "C" int dbot_b200_n_slots(dbot_b200_sensor* s) { return s ? s->n_slots : -1; }
 extern "C" double dbot_b200_observation_time(dbot_b200_sensor* s) { return s ? s->t_obs : NAN; }
+
+/* ---- occlusion-slot migration between handles (cross-GPU resampling) ---- */
+__global__ void dbot_export_slot_kernel(const float* __restrict__ pool, const int32_t* __restrict__ loc,
+                                        int slot, size_t slot_stride, float* __restrict__ dst)
+{
+    const float4* src = reinterpret_cast<const float4*>(pool + (size_t)loc[slot] * slot_stride);
+    float4* out = reinterpret_cast<float4*>(dst);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < slot_stride / 4;
+         i += (size_t)gridDim.x * blockDim.x)
+        out[i] = src[i];
+}
+__global__ void dbot_import_pop_kernel(int32_t* loc, int32_t* free_stack, int32_t* free_count, int slot,
+                                       int* err_flag)
+{
+    const int f = *free_count;
+    if (f <= 0)
+    {
+        atomicExch(err_flag, 2);
+        loc[slot] = loc[0];
+        return;
+    }
+    loc[slot] = free_stack[f - 1];
+    *free_count = f - 1;
+}
+__global__ void dbot_import_copy_kernel(float* __restrict__ pool, const int32_t* __restrict__ loc, int slot,
+                                        size_t slot_stride, const float* __restrict__ src)
+{
+    float4* out = reinterpret_cast<float4*>(pool + (size_t)loc[slot] * slot_stride);
+    const float4* in = reinterpret_cast<const float4*>(src);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < slot_stride / 4;
+         i += (size_t)gridDim.x * blockDim.x)
+        out[i] = in[i];
+}
+
+extern "C" int64_t dbot_b200_slot_floats(dbot_b200_sensor* s) { return s ? (int64_t)s->kp.slot_stride : -1; }
+
+extern "C" int dbot_b200_export_slot_device(dbot_b200_sensor* s, int32_t slot, float* d_dst)
+{
+    if (!s || !d_dst) return fail(-1, "export_slot: null argument");
+    if (slot < 0 || slot >= s->n_slots) return fail(-7, "export_slot: slot %d of %d", slot, s->n_slots);
+    CUDA_TRY(cudaSetDevice(s->device));
+    dbot_export_slot_kernel<<<64, 256, 0, s->stream>>>(s->d_pool, s->d_loc[s->cur], slot, s->kp.slot_stride, d_dst);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dbot_b200_import_slot_device(dbot_b200_sensor* s, const float* d_src, int32_t* out_slot)
+{
+    if (!s || !d_src || !out_slot) return fail(-1, "import_slot: null argument");
+    /* live + imported slots stay within half of the pool, so that an update can always find a fresh
+     * slot for every copying child (every imported slot is some child's parent and is adopted) */
+    if (s->n_slots >= 2 * s->cfg.max_particles - 1)
+        return fail(-2, "import_slot: %d slots are live, the pool holds %d", s->n_slots, 2 * s->cfg.max_particles);
+    CUDA_TRY(cudaSetDevice(s->device));
+    const int slot = s->n_slots;
+    dbot_import_pop_kernel<<<1, 1, 0, s->stream>>>(s->d_loc[s->cur], s->d_free, s->d_free_count, slot, s->d_err);
+    dbot_import_copy_kernel<<<64, 256, 0, s->stream>>>(s->d_pool, s->d_loc[s->cur], slot, s->kp.slot_stride, d_src);
+    s->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    s->n_slots = slot + 1;
+    *out_slot = slot;
+    return 0;
+}
 
 extern "C" int dbot_b200_free_slot_count(dbot_b200_sensor* s)
 {

@@ -289,6 +289,19 @@ class B200KinectImageModel(RbSensor):
     def synchronize(self):
         abi.check(self._lib, self._lib.dbot_b200_synchronize(self._h))
 
+    # -- occlusion-slot migration (particle-sharded filter, cross-GPU parents) -------------------
+    @property
+    def slot_floats(self):
+        return int(self._lib.dbot_b200_slot_floats(self._h))
+
+    def export_slot_device(self, slot, d_dst_ptr):
+        abi.check(self._lib, self._lib.dbot_b200_export_slot_device(self._h, int(slot), C.c_void_p(d_dst_ptr)))
+
+    def import_slot_device(self, d_src_ptr):
+        out = C.c_int32(-1)
+        abi.check(self._lib, self._lib.dbot_b200_import_slot_device(self._h, C.c_void_p(d_src_ptr), C.byref(out)))
+        return out.value
+
     @property
     def stream(self):
         return self._lib.dbot_b200_stream(self._h)

@@ -3,18 +3,22 @@
 Particles are independent, so rank g of G evaluates the contiguous slice [lo_g, hi_g) of every
 `loglikes` call on its own sensor and owns the occlusion slots of exactly those particles.  The
 depth frame, the mesh and the camera are replicated (every rank calls set_observation with the
-same image).  The one exchange step of the path is an all-gather of the log-weights, so that every
-rank -- each runs the same filter -- sees all N weights and takes the same resampling decision.
-There is no other collective on the data path.
+same image).  The one exchange step of the evaluation is an all-gather of the log-weights, so that
+every rank -- each runs the same filter -- sees all N weights and takes the same resampling
+decision.
 
 `indices` keeps the reference's meaning (occlusion slot of each particle's parent, global
-numbering; ref semantics in SURVEY.md A.5).  A parent slot that lives on another rank would need
-its 4*P-byte occlusion image moved over NVLink first; this class refuses such a call with
-CrossShardParent instead of computing something else.
+numbering).  After a resampling step a child may have its parent on another rank
+(SURVEY.md section 8f row N2): the parent's occlusion image then migrates first -- the owner
+exports the slot, it travels point to point (NCCL send/recv over NVLink on GPUs), the receiver
+imports it as an extra local slot that the child names as its parent; like every parent slot it is
+dropped (or adopted) by the next update.  Every rank sees the same global `indices`, so every rank
+derives the same transfer schedule without negotiation.  `allow_migration=False` refuses such calls
+instead (CrossShardParent), which is what BASELINE config 4 (shard-local parents) needs.
 
-The local sensor is anything with reset / set_observation / loglikes_poses / compose -- in the
-product the B200KinectImageModel; the CPU test-suite injects the oracle to check the host logic
-under gloo.
+The local sensor is anything with reset / set_observation / loglikes_poses / compose and the slot
+export / import pair -- in the product the B200KinectImageModel (device-pointer variants); the CPU
+test-suite injects the oracle to check the host logic under gloo.
 """
 from __future__ import annotations
 
@@ -38,8 +42,17 @@ def shard_counts(n, world):
     return [shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0] for r in range(world)]
 
 
+def shard_owner(slot, n, world):
+    """rank that owns item `slot` of n (inverse of shard_bounds)"""
+    base, extra = divmod(int(n), int(world))
+    cut = extra * (base + 1)
+    if slot < cut:
+        return int(slot // (base + 1))
+    return int(extra + (slot - cut) // max(base, 1))
+
+
 class ShardedRbSensor(RbSensor):
-    def __init__(self, local_sensor, group=None, device=None):
+    def __init__(self, local_sensor, group=None, device=None, allow_migration=True):
         import torch
         import torch.distributed as dist
 
@@ -53,13 +66,21 @@ class ShardedRbSensor(RbSensor):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
         self.device = device
+        self.allow_migration = allow_migration
         self.n_slots = 1          # global slot count; after reset every rank holds slot 0
         self._buf = None
+        # parents imported since the last update: for EVERY rank the set of global slots it holds a
+        # copy of (all ranks track all sets: the schedule must come out the same everywhere), and for
+        # this rank the local slot index of each
+        self._imported_keys = [set() for _ in range(self.world)]
+        self._imported_local = {}
+        self.migrated_slots = 0   # slots this rank has received so far (statistics)
 
     # -- RbSensor ---------------------------------------------------------------------------
     def reset(self):
         self.local.reset()
         self.n_slots = 1
+        self._forget_imports()
 
     def set_observation(self, image):
         self.local.set_observation(image)
@@ -68,21 +89,108 @@ class ShardedRbSensor(RbSensor):
         return self.loglikes_poses(self.local.compose(deltas), indices, update)
 
     # -- pieces ------------------------------------------------------------------------------
+    def _forget_imports(self):
+        self._imported_keys = [set() for _ in range(self.world)]
+        self._imported_local = {}
+
+    def transfer_schedule(self, indices, n):
+        """{(owner, needer): sorted global parent slots} for the parents that live on another rank
+        than their children and have not been imported there yet -- identical on every rank"""
+        sched = {}
+        if self.n_slots == 1:
+            return sched
+        for r in range(self.world):
+            lo, hi = shard_bounds(n, self.world, r)
+            plo, phi = shard_bounds(self.n_slots, self.world, r)
+            par = np.unique(np.asarray(indices[lo:hi], dtype=np.int64))
+            for s in par[(par < plo) | (par >= phi)]:
+                s = int(s)
+                if s in self._imported_keys[r]:
+                    continue
+                sched.setdefault((shard_owner(s, self.n_slots, self.world), r), []).append(s)
+        return sched
+
+    def _export(self, local_slots):
+        """stored images of local slots as one [k, slot_floats] tensor on self.device"""
+        import torch
+
+        F = self.local.slot_floats
+        if self.device.type == "cuda":
+            buf = torch.empty((len(local_slots), F), dtype=torch.float32, device=self.device)
+            for j, s in enumerate(local_slots):
+                self.local.export_slot_device(s, buf[j].data_ptr())
+            self.local.synchronize()       # exports run on the library's stream, the send on torch's
+            return buf
+        return torch.from_numpy(np.stack([np.asarray(self.local.export_slot(s), dtype=np.float32)
+                                          for s in local_slots]))
+
+    def _import(self, buf):
+        import torch
+
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()   # the receive has landed
+            out = [self.local.import_slot_device(buf[j].data_ptr()) for j in range(buf.shape[0])]
+            self.local.synchronize()       # buf may be released after this
+            return out
+        return [self.local.import_slot(buf[j].numpy()) for j in range(buf.shape[0])]
+
+    def migrate(self, indices, n):
+        """move every remote parent of this rank's children here (point to point, one message per
+        owner/needer pair); returns the number of slots received"""
+        import torch
+        import torch.distributed as dist
+
+        sched = self.transfer_schedule(indices, n)
+        if not sched:
+            return 0
+        if not self.allow_migration:
+            (o, r), slots = sorted(sched.items())[0]
+            raise CrossShardParent(
+                "rank %d needs occlusion slot %d, which rank %d owns; migration is disabled" % (r, slots[0], o))
+        F = self.local.slot_floats
+        ops, recv = [], []
+        keep = []
+        plo, _ = shard_bounds(self.n_slots, self.world, self.rank)
+        for (o, r), slots in sorted(sched.items()):
+            if o == self.rank:
+                buf = self._export([s - plo for s in slots])
+                keep.append(buf)
+                ops.append(dist.P2POp(dist.isend, buf, self._peer(r), group=self.group))
+            elif r == self.rank:
+                buf = torch.empty((len(slots), F), dtype=torch.float32, device=self.device)
+                recv.append((slots, buf))
+                ops.append(dist.P2POp(dist.irecv, buf, self._peer(o), group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        got = 0
+        for slots, buf in recv:
+            for s, local_idx in zip(slots, self._import(buf)):
+                self._imported_local[s] = local_idx
+            got += len(slots)
+        for (o, r), slots in sched.items():
+            self._imported_keys[r].update(slots)
+        self.migrated_slots += got
+        return got
+
+    def _peer(self, r):
+        import torch.distributed as dist
+
+        return r if self.group is None else dist.get_global_rank(self.group, r)
+
     def local_parents(self, indices, n):
-        """global parent slots of this rank's particles -> local slot numbers"""
+        """global parent slots of this rank's particles -> local slot numbers (after migrate())"""
         lo, hi = shard_bounds(n, self.world, self.rank)
         parents = np.asarray(indices[lo:hi], dtype=np.int64)
-        if np.any(parents < 0) or np.any(parents >= self.n_slots):
+        if np.any(np.asarray(indices) < 0) or np.any(np.asarray(indices) >= self.n_slots):
             raise IndexError("loglikes: parent slot out of range (have %d)" % self.n_slots)
         if self.n_slots == 1:
             return lo, hi, np.zeros(hi - lo, dtype=np.int32)
         plo, phi = shard_bounds(self.n_slots, self.world, self.rank)
-        if np.any(parents < plo) or np.any(parents >= phi):
-            bad = parents[(parents < plo) | (parents >= phi)][0]
-            raise CrossShardParent(
-                "rank %d owns occlusion slots [%d,%d) but a particle of its shard has parent %d; "
-                "cross-rank occlusion-row migration is not implemented" % (self.rank, plo, phi, bad))
-        return lo, hi, (parents - plo).astype(np.int32)
+        out = np.empty(hi - lo, dtype=np.int32)
+        for k, s in enumerate(parents):
+            out[k] = s - plo if plo <= s < phi else self._imported_local[int(s)]
+        return lo, hi, out
 
     def all_gather(self, local_values, n):
         """all-gather of ragged shards: pad to the largest shard, one collective, unpad"""
@@ -108,10 +216,14 @@ class ShardedRbSensor(RbSensor):
         n = poses.shape[0]
         if not (isinstance(indices, np.ndarray) and indices.dtype == np.int32 and indices.size == n):
             raise TypeError("loglikes: indices must be an int32 numpy array with one entry per state")
+        if np.any(indices < 0) or np.any(indices >= self.n_slots):
+            raise IndexError("loglikes: parent slot out of range (have %d)" % self.n_slots)
+        self.migrate(indices, n)
         lo, hi, local_idx = self.local_parents(indices, n)
         mine = self.local.loglikes_poses(poses[lo:hi], local_idx, update) if hi > lo else np.zeros(0)
         out = self.all_gather(mine, n)
         if update:
             indices[:] = np.arange(n, dtype=np.int32)
             self.n_slots = n
+            self._forget_imports()
         return out

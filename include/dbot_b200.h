@@ -95,6 +95,16 @@ int dbot_b200_loglikes_device(dbot_b200_sensor* s, const float* d_poses, int32_t
 void* dbot_b200_stream(dbot_b200_sensor* s); /* cudaStream_t */
 int dbot_b200_synchronize(dbot_b200_sensor* s);
 
+/* ---- occlusion-slot migration between handles (particle-sharded filter: a child whose parent lives
+ * on another GPU).  Both handles must be at the same observation / update
+ * time (they are when every rank runs the same call sequence).  d_dst / d_src: device buffers of
+ * dbot_b200_slot_floats() floats; work is enqueued on the handle's stream. ---- */
+int64_t dbot_b200_slot_floats(dbot_b200_sensor* s);
+int dbot_b200_export_slot_device(dbot_b200_sensor* s, int32_t slot, float* d_dst);
+/* appends a logical slot (index returned in *out_slot) that the next loglikes calls may name as a
+ * parent; like every slot it is dropped by the next update unless a child adopts it */
+int dbot_b200_import_slot_device(dbot_b200_sensor* s, const float* d_src, int32_t* out_slot);
+
 /* ---- state read-back (tests, debugging) ---- */
 int dbot_b200_n_slots(dbot_b200_sensor* s);
 double dbot_b200_observation_time(dbot_b200_sensor* s);

@@ -468,6 +468,25 @@ int oracle_get_occlusion_raw(const oracle_sensor* s, int32_t slot, float* out_oc
     return 0;
 }
 
+/* TEST SUPPORT for the particle-sharded evaluator: append a slot holding an occlusion image (and its
+ * per-pixel time stamps) exported from another oracle instance with oracle_get_occlusion_raw.
+ * Returns the new slot index. */
+int oracle_import_slot(oracle_sensor* s, const float* occ, const double* occ_time)
+{
+    if (!s || !occ || !occ_time) return -1;
+    const size_t P = (size_t)s->P, n = (size_t)s->n_slots;
+    float* no = (float*)realloc(s->occ, sizeof(float) * P * (n + 1));
+    if (!no) return -5;
+    s->occ = no;
+    double* nt = (double*)realloc(s->occ_time, sizeof(double) * P * (n + 1));
+    if (!nt) return -5;
+    s->occ_time = nt;
+    memcpy(s->occ + P * n, occ, sizeof(float) * P);
+    memcpy(s->occ_time + P * n, occ_time, sizeof(double) * P);
+    s->n_slots = (int)n + 1;
+    return (int)n;
+}
+
 void oracle_set_num_threads(int n)
 {
 #ifdef _OPENMP

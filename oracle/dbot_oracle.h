@@ -85,6 +85,9 @@ double oracle_p_occluded(const oracle_sensor* s, double y, double d);
 double oracle_p_occluded_inf(const oracle_sensor* s, double y);
 double oracle_propagate(const oracle_sensor* s, double o, double dt);
 
+/* test support: append a slot exported from another instance (see dbot_oracle.c) */
+int oracle_import_slot(oracle_sensor* s, const float* occ, const double* occ_time);
+
 #ifdef __cplusplus
 }
 #endif

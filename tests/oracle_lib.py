@@ -84,6 +84,7 @@ def oracle_lib():
         lib.oracle_observation_time.restype = C.c_double
         lib.oracle_get_occlusion.argtypes = [P, C.c_int32, P]
         lib.oracle_get_occlusion_raw.argtypes = [P, C.c_int32, P, P]
+        lib.oracle_import_slot.argtypes = [P, P, P]
         lib.oracle_set_num_threads.argtypes = [C.c_int]
         lib.oracle_get_max_threads.restype = C.c_int
         for f in ("oracle_p_visible", "oracle_p_occluded", "oracle_propagate"):
@@ -168,6 +169,24 @@ class Oracle:
         t = np.empty(self.rows * self.cols, dtype=np.float64)
         assert self.lib.oracle_get_occlusion_raw(self.h, slot, abi.ptr(o), abi.ptr(t)) == 0
         return o.reshape(self.rows, self.cols), t.reshape(self.rows, self.cols)
+
+    # -- slot migration, as the sharded evaluator drives it (payload: float32 vector) -----------
+    @property
+    def slot_floats(self):
+        return 3 * self.rows * self.cols           # P floats + P doubles
+
+    def export_slot(self, slot):
+        o, t = self.occlusion_raw(slot)
+        return np.concatenate([o.reshape(-1), t.reshape(-1).view(np.float32)])
+
+    def import_slot(self, payload):
+        P = self.rows * self.cols
+        payload = np.ascontiguousarray(payload, dtype=np.float32)
+        o = np.ascontiguousarray(payload[:P])
+        t = np.ascontiguousarray(payload[P:]).view(np.float64)
+        idx = self.lib.oracle_import_slot(self.h, abi.ptr(o), abi.ptr(t))
+        assert idx >= 0
+        return idx
 
     def close(self):
         if self.h:

@@ -36,7 +36,7 @@ def shard_local_parents(n, world, rng):
     return out
 
 
-def run(sensor, n, frames, world, seed, render):
+def run(sensor, n, frames, world, seed, render, global_parents=False):
     rows, cols, K, V, T, rng, gt = scenario(n, frames, seed)
     idx = np.zeros(n, dtype=np.int32)
     outs = []
@@ -44,7 +44,10 @@ def run(sensor, n, frames, world, seed, render):
         frame = synth.make_frame(render, gt, rows, cols, rng)
         poses = synth.particle_poses(gt, n, rng)
         if f > 0:
-            idx = shard_local_parents(n, world, rng)
+            # global_parents: sorted draws from all slots, as systematic resampling over the whole
+            # particle set produces them -- children get parents on other ranks
+            idx = (np.sort(rng.integers(0, n, size=n)).astype(np.int32) if global_parents
+                   else shard_local_parents(n, world, rng))
         sensor.set_observation(frame)
         outs.append(sensor.loglikes_poses(poses, idx, update=False))
         outs.append(sensor.loglikes_poses(poses, idx, update=True))
@@ -60,19 +63,25 @@ def main():
     local = oracle_lib.Oracle(rows, cols, K, V, T, synth.default_parameters())
     sensor = ShardedRbSensor(local)
     got = run(sensor, n, frames, world, seed, local.render)
-    # a parent on the other rank must be refused, not silently evaluated
+    # with migration disabled a parent on the other rank must be refused, not silently evaluated
     refused = False
     bad = np.arange(n, dtype=np.int32)[::-1].copy()
+    strict = ShardedRbSensor(local, allow_migration=False)
+    strict.n_slots = sensor.n_slots
     try:
-        sensor.loglikes_poses(np.zeros((n, 1, 12), np.float32), bad, update=False)
+        strict.loglikes_poses(np.zeros((n, 1, 12), np.float32), bad, update=False)
     except CrossShardParent:
         refused = True
+    # cross-rank resampling: parents migrate between the ranks
+    sensor.reset()
+    got_global = run(sensor, n, frames, world, seed + 1, local.render, global_parents=True)
+    migrated = sensor.migrated_slots
     flags = [None] * world
     dist.all_gather_object(flags, refused)
     sensor.reset()
     assert sensor.n_slots == 1
     np.savez(out_path + ".rank%d.npz" % rank, got=got, refused=np.array(flags), lo_hi=np.array(shard_bounds(n, world, rank)),
-             local_slots=local.n_slots)
+             local_slots=local.n_slots, got_global=got_global, migrated=migrated)
     dist.destroy_process_group()
 
 

@@ -12,7 +12,7 @@ import pytest
 import oracle_lib
 import sharded_worker
 from dbot_ros_b200 import synth
-from dbot_ros_b200.sharded import shard_bounds, shard_counts
+from dbot_ros_b200.sharded import shard_bounds, shard_counts, shard_owner
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -31,6 +31,9 @@ def test_shard_bounds_partition():
             assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
             c = shard_counts(n, world)
             assert sum(c) == n and max(c) - min(c) <= 1
+            for slot in set([0, n // 3, n // 2, max(n - 1, 0)]) if n else ():
+                r = shard_owner(slot, n, world)
+                assert b[r][0] <= slot < b[r][1]
 
 
 @pytest.mark.parametrize("n", [37, 64])  # ragged and even shards
@@ -47,10 +50,17 @@ def test_two_ranks_match_one_process(tmp_path, n):
     rows, cols, K, V, T, _, _ = sharded_worker.scenario(n, frames, seed)
     orc = oracle_lib.Oracle(rows, cols, K, V, T, synth.default_parameters())
     want = sharded_worker.run(orc, n, frames, world, seed, orc.render)
+    orc.reset()
+    want_global = sharded_worker.run(orc, n, frames, world, seed + 1, orc.render, global_parents=True)
+    migrated = 0
     for rank in range(world):
         z = np.load(out + ".rank%d.npz" % rank)
         assert np.array_equal(z["got"], want), "rank %d differs from the unsharded evaluation" % rank
+        # parents drawn from all slots: occlusion images migrated between the ranks, results unchanged
+        assert np.array_equal(z["got_global"], want_global), "rank %d: cross-rank parents" % rank
+        migrated += int(z["migrated"])
         assert z["refused"].all()
         lo, hi = z["lo_hi"]
         assert int(z["local_slots"]) == 1  # reset collapsed the local state again
         assert (lo, hi) == shard_bounds(n, world, rank)
+    assert migrated > 0  # the scenario did move occlusion images between the ranks

@@ -1,5 +1,6 @@
 """-m gpu: the particle-sharded evaluator over NCCL on 2 GPUs (skipped on a 1-GPU box): sharding
-must not change a single bit of any log-weight."""
+must not change a single bit of any log-weight, with shard-local parents and
+with parents that migrate between the GPUs."""
 import os
 import subprocess
 import sys
@@ -30,14 +31,16 @@ rng = np.random.default_rng(5)
 gt = synth.ground_truth_poses(1, rng)
 ok = True
 idx = np.zeros(n, dtype=np.int32)
-for f in range(3):
+for f in range(5):
     frame = synth.make_frame(local.render, gt, rows, cols, rng)
     poses = synth.particle_poses(gt, n, rng)
-    if f > 0:
+    if f in (1, 2):      # shard-local parents (BASELINE config 4)
         idx = np.empty(n, dtype=np.int32)
         for r in range(world):
             lo, hi = shard_bounds(n, world, r)
             idx[lo:hi] = rng.integers(lo, hi, size=hi - lo)
+    elif f > 2:          # global resampling: occlusion images migrate over NVLink
+        idx = np.sort(rng.integers(0, n, size=n)).astype(np.int32)
     i1, i2 = idx.copy(), idx.copy()
     sharded.set_observation(frame)
     got = sharded.loglikes_poses(poses, i1, True)
@@ -45,6 +48,9 @@ for f in range(3):
         single.set_observation(frame)
         want = single.loglikes_poses(poses, i2, True)
         ok = ok and np.array_equal(got, want) and np.array_equal(i1, i2)
+moved = torch.tensor([sharded.migrated_slots], device="cuda")
+dist.all_reduce(moved)
+ok = ok and int(moved.item()) > 0
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
