@@ -99,6 +99,14 @@ class ShardedRbSensor(RbSensor):
         sched = {}
         if self.n_slots == 1:
             return sched
+        # fast path (the common case): every parent lives on its child's rank
+        idx = np.asarray(indices, dtype=np.int64)
+        c_hi = np.array([shard_bounds(n, self.world, r)[1] for r in range(self.world)])
+        p_hi = np.array([shard_bounds(self.n_slots, self.world, r)[1] for r in range(self.world)])
+        child_rank = np.searchsorted(c_hi, np.arange(n), side="right")
+        parent_rank = np.searchsorted(p_hi, idx, side="right")
+        if np.array_equal(child_rank, parent_rank):
+            return sched
         for r in range(self.world):
             lo, hi = shard_bounds(n, self.world, r)
             plo, phi = shard_bounds(self.n_slots, self.world, r)
