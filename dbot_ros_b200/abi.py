@@ -46,6 +46,19 @@ class Config(C.Structure):
     ]
 
 
+class FilterConfig(C.Structure):
+    """dbot_b200_filter_config (include/dbot_b200.h)"""
+
+    _fields_ = [
+        ("linear_sigma", C.c_double * 3),
+        ("angular_sigma", C.c_double * 3),
+        ("velocity_factor", C.c_double),
+        ("max_kl_divergence", C.c_double),
+        ("seed", C.c_uint64),
+        ("n_particles", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/dbot_b200.h declares
 _P = C.c_void_p
 SIGNATURES = {
@@ -62,6 +75,10 @@ SIGNATURES = {
     "dbot_b200_slot_floats": (C.c_int64, [_P]),
     "dbot_b200_export_slot_device": (C.c_int, [_P, C.c_int32, _P]),
     "dbot_b200_import_slot_device": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
+    "dbot_b200_filter_create": (C.c_int, [_P, C.POINTER(FilterConfig), C.POINTER(_P)]),
+    "dbot_b200_filter_destroy": (C.c_int, [_P]),
+    "dbot_b200_filter_initialize": (C.c_int, [_P, _P]),
+    "dbot_b200_filter_track": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int32)]),
     "dbot_b200_n_slots": (C.c_int, [_P]),
     "dbot_b200_observation_time": (C.c_double, [_P]),
     "dbot_b200_free_slot_count": (C.c_int, [_P]),

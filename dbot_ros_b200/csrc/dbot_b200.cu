@@ -1672,3 +1672,5 @@ extern "C" int dbot_b200_profile_read(dbot_b200_sensor* s, float* out_ms, int64_
 }
 extern "C" int64_t dbot_b200_launch_count(dbot_b200_sensor* s) { return s ? s->launches : -1; }
 extern "C" int64_t dbot_b200_device_bytes(dbot_b200_sensor* s) { return s ? s->device_bytes : -1; }
+
+#include "dbot_filter.cuh"

@@ -47,6 +47,46 @@ class TrackerParameters:
     transition: ObjectTransitionParameters = field(default_factory=ObjectTransitionParameters)
 
 
+# ---- counter-based noise shared with the device-resident filter (csrc/dbot_filter.cuh) ----------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(x):
+    with np.errstate(over="ignore"):
+        x = (np.asarray(x, dtype=np.uint64) + np.uint64(0x9E3779B97F4A7C15)) & _M64
+        x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        return x ^ (x >> np.uint64(31))
+
+
+def noise_key(seed, frame, block, particle, pair):
+    with np.errstate(over="ignore"):
+        base = splitmix64(np.uint64(seed) ^ ((np.uint64(frame) * np.uint64(0x100000001B3)) & _M64))
+        return (base ^ (np.uint64(block) << np.uint64(56)) ^ (np.asarray(particle, dtype=np.uint64) << np.uint64(8))
+                ^ np.uint64(pair))
+
+
+def counter_normals(seed, frame, block, n):
+    """[n][6] standard normals exactly as dbot_filter_propagate_kernel draws them (Box-Muller on two
+    splitmix64 outputs per pair; equal up to the last bits of log/sincos)"""
+    out = np.empty((n, 6))
+    particles = np.arange(n, dtype=np.uint64)
+    for pair in range(3):
+        h1 = splitmix64(noise_key(seed, frame, block, particles, pair))
+        h2 = splitmix64(h1)
+        u1 = ((h1 >> np.uint64(11)).astype(np.float64) + 1.0) / 9007199254740992.0
+        u2 = (h2 >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+        r = np.sqrt(-2.0 * np.log(u1))
+        out[:, 2 * pair] = r * np.cos(2.0 * np.pi * u2)
+        out[:, 2 * pair + 1] = r * np.sin(2.0 * np.pi * u2)
+    return out
+
+
+def counter_uniform(seed, frame, block):
+    h = splitmix64(noise_key(seed, frame, block, 0x7FFFFF, 7))
+    return float((h >> np.uint64(11)).astype(np.float64) / 9007199254740992.0)
+
+
 def systematic_resample(weights, n, u0):
     """n parents from normalised weights with one uniform draw (sorted output)"""
     cdf = np.cumsum(weights)
@@ -60,10 +100,15 @@ class ParticleTracker:
     ref:source/dbot_ros/object_tracker_ros.hpp:49).  States are deltas relative to the sensor's
     integrated poses: [n][n_obj][12] = position, rotation vector, linear velocity, angular velocity."""
 
-    def __init__(self, sensor, n_objects, params: TrackerParameters, seed=0):
+    def __init__(self, sensor, n_objects, params: TrackerParameters, seed=0, counter_noise=False):
+        """counter_noise: draw the noise from the counter-based generator of the device-resident
+        filter (same seed -> same noise on both) instead of numpy's generator"""
         self.sensor = sensor
         self.n_obj = int(n_objects)
         self.p = params
+        self.seed = int(seed)
+        self.counter_noise = counter_noise
+        self.frame = 0
         self.rng = np.random.default_rng(seed)
         self.n = max(1, params.evaluation_count // self.n_obj)   # SURVEY.md A.7
         self.states = np.zeros((self.n, self.n_obj, 12))
@@ -81,6 +126,7 @@ class ParticleTracker:
         self.log_w[:] = -np.log(self.n)
         self.indices[:] = 0
         self.loglikes[:] = 0.0
+        self.frame = 0
         self.sensor.reset()
 
     # -- RBC-PF::filter -----------------------------------------------------------------------
@@ -90,7 +136,8 @@ class ParticleTracker:
 
     def resample(self):
         w = np.exp(self.log_w)
-        parents = systematic_resample(w / w.sum(), self.n, self.rng.random())
+        u0 = counter_uniform(self.seed, self.frame, self._block) if self.counter_noise else self.rng.random()
+        parents = systematic_resample(w / w.sum(), self.n, u0)
         self.states = self.states[parents]
         self.next_states = self.next_states[parents]
         self.noise = self.noise[parents]
@@ -114,7 +161,9 @@ class ParticleTracker:
         self.noise = np.zeros((self.n, self.n_obj, 6))
         self.next_states = self.states
         for block in range(self.n_obj):                 # one sampling block per object
-            self.noise[:, block, :] = self.rng.standard_normal((self.n, 6))
+            self._block = block
+            self.noise[:, block, :] = (counter_normals(self.seed, self.frame, block, self.n) if self.counter_noise
+                                       else self.rng.standard_normal((self.n, 6)))
             self.next_states = self.propagate(self.states, self.noise)
             update = block == self.n_obj - 1
             new = self.sensor.loglikes(self.next_states.reshape(self.n, -1), self.indices, update)
@@ -124,6 +173,7 @@ class ParticleTracker:
             if self.kl_given_uniform() > self.p.max_kl_divergence:
                 self.resample()
         self.states = self.next_states
+        self.frame += 1
 
     # -- ParticleTracker::on_track + Tracker::track -------------------------------------------
     def track(self, image):
@@ -161,3 +211,56 @@ def rotation_vectors(R):
     s = np.sin(angle)
     scale = np.where(s > 1e-9, angle / np.where(s > 1e-9, 2.0 * s, 1.0), 0.5)
     return v * scale[..., None]
+
+
+class DeviceParticleTracker:
+    """The same tracker with the whole filter step on the GPU (libdbot_b200.so, dbot_b200_filter_*):
+    per frame the depth image goes in and the integrated poses come out; particles, poses, parent
+    indices and weights never leave HBM."""
+
+    def __init__(self, sensor, params: TrackerParameters, seed=0):
+        import ctypes as C
+
+        from . import abi
+
+        self._C, self._abi = C, abi
+        self.sensor = sensor
+        self.n_obj = sensor.n_objects
+        self.n = max(1, params.evaluation_count // self.n_obj)
+        cfg = abi.FilterConfig()
+        for k in range(3):
+            cfg.linear_sigma[k] = params.transition.linear_sigma[k]
+            cfg.angular_sigma[k] = params.transition.angular_sigma[k]
+        cfg.velocity_factor = params.transition.velocity_factor
+        cfg.max_kl_divergence = params.max_kl_divergence
+        cfg.seed = int(seed)
+        cfg.n_particles = self.n
+        self._lib = sensor._lib
+        self._h = C.c_void_p()
+        abi.check(self._lib, self._lib.dbot_b200_filter_create(sensor._h, C.byref(cfg), C.byref(self._h)))
+        self.resample_count = 0
+
+    def initialize(self, initial_poses):
+        poses = np.ascontiguousarray(initial_poses, dtype=np.float64).reshape(self.n_obj, 6)
+        self._abi.check(self._lib, self._lib.dbot_b200_filter_initialize(self._h, self._abi.ptr(poses)))
+        self.resample_count = 0
+
+    def track(self, image):
+        img = np.ascontiguousarray(image, dtype=np.float32).reshape(-1)
+        out = np.empty((self.n_obj, 6), dtype=np.float64)
+        cnt = self._C.c_int32(0)
+        self._abi.check(self._lib, self._lib.dbot_b200_filter_track(self._h, self._abi.ptr(img), self._abi.ptr(out),
+                                                                   self._C.byref(cnt)))
+        self.resample_count = cnt.value
+        return out
+
+    def close(self):
+        if self._h:
+            self._lib.dbot_b200_filter_destroy(self._h)
+            self._h = self._C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -105,6 +105,30 @@ int dbot_b200_export_slot_device(dbot_b200_sensor* s, int32_t slot, float* d_dst
  * parent; like every slot it is dropped by the next update unless a child adopts it */
 int dbot_b200_import_slot_device(dbot_b200_sensor* s, const float* d_src, int32_t* out_slot);
 
+/* ---- device-resident filter step around the sensor: dbot's
+ * RaoBlackwellCoordinateParticleFilter::filter + ParticleTracker::on_track, i.e. what
+ * tracker->initialize(poses) / tracker->track(image) run per frame
+ * (ref:source/dbot_ros/tracker/particle_tracker_node.cpp:252, ref:source/dbot_ros/object_tracker_ros.hpp:49),
+ * with every O(N) step as a kernel on the sensor's stream: states, poses, parent indices and weights
+ * stay in HBM; per frame the depth image goes in and n_objects * 6 doubles come out. ---- */
+typedef struct dbot_b200_filter dbot_b200_filter; /* opaque */
+typedef struct
+{
+    double linear_sigma[3], angular_sigma[3]; /* ref:config/particle_tracker.yaml:55-60 */
+    double velocity_factor;                   /* ref:config/particle_tracker.yaml:63 */
+    double max_kl_divergence;                 /* ref:config/particle_tracker.yaml:36 */
+    uint64_t seed;                            /* counter-based noise: same seed, same track */
+    int32_t n_particles;                      /* evaluation_count / n_objects, <= max_particles */
+} dbot_b200_filter_config;
+int dbot_b200_filter_create(dbot_b200_sensor* s, const dbot_b200_filter_config* cfg, dbot_b200_filter** out);
+int dbot_b200_filter_destroy(dbot_b200_filter* f);
+/* poses: [n_objects][6] position + rotation vector in the camera frame; resets the sensor */
+int dbot_b200_filter_initialize(dbot_b200_filter* f, const double* poses);
+/* out_poses: [n_objects][6] integrated poses after this frame; out_resamplings (optional): number of
+ * resampling steps since initialize */
+int dbot_b200_filter_track(dbot_b200_filter* f, const float* depth_m, double* out_poses,
+                           int32_t* out_resamplings);
+
 /* ---- state read-back (tests, debugging) ---- */
 int dbot_b200_n_slots(dbot_b200_sensor* s);
 double dbot_b200_observation_time(dbot_b200_sensor* s);

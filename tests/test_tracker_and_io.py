@@ -103,3 +103,60 @@ def test_tracker_on_the_cuda_sensor_follows_the_object():
     err = np.linalg.norm(est - truth, axis=1)
     assert err[-10:].max() < 0.003, err                            # within 3 mm while it moves 2.7 mm/frame
     assert sensor.n_slots == 400 and tr.resample_count >= 1
+
+
+def test_counter_noise_is_standard_normal_and_reproducible():
+    from dbot_ros_b200.tracker import counter_normals, counter_uniform
+
+    z = counter_normals(7, 2, 1, 50000)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
+    assert np.abs(np.corrcoef(z.T) - np.eye(6)).max() < 0.02
+    assert np.array_equal(z[:100], counter_normals(7, 2, 1, 100))          # a function of its counters only
+    assert not np.allclose(z[:100], counter_normals(7, 3, 1, 100))
+    assert 0.0 <= counter_uniform(7, 2, 1) < 1.0
+
+
+@pytest.mark.gpu
+def test_device_resident_filter_matches_the_host_loop_and_tracks():
+    """dbot_b200_filter_*: the whole filter step on the GPU.  With the same counter-based noise the
+    host loop (numpy, driving an identical sensor) must produce the same track; two objects so that
+    there are two sampling blocks per frame."""
+    from dbot_ros_b200.tracker import DeviceParticleTracker
+
+    rows, cols = synth.resolution(4)
+    K = synth.camera_matrix(4)
+    a = synth.icosphere(2, radius=0.05, seed=4)
+    b = synth.torus(24, 12, R=0.05, r=0.02)
+    V, T = [a[0], b[0]], [a[1], b[1]]
+    n_eval = 600                                                  # 300 particles per object block
+    mk = lambda: RbSensorBuilder(ObjectModel(V, T), CameraData(K, rows, cols), Parameters(sample_count=300)).build()  # noqa: E731
+    s_dev, s_host = mk(), mk()
+    rng = np.random.default_rng(12)
+    start = np.array([[-0.08, 0.0, 0.75, 0.0, 0.0, 0.0], [0.09, 0.01, 0.85, 0.3, -0.2, 0.1]])
+    step = np.array([[0.0015, -0.001, 0.001, 0, 0, 0.01], [-0.001, 0.001, -0.0015, 0, 0.01, 0]])
+    frames, truth = [], []
+    for f in range(12):
+        pose = start + f * step
+        gt = [(synth.rodrigues(pose[o, 3:6]), pose[o, 0:3]) for o in range(2)]
+        frames.append(synth.make_frame(s_dev.render, gt, rows, cols, rng, occluder=False))
+        truth.append(pose[:, :3].copy())
+    prm = TrackerParameters(evaluation_count=n_eval)
+    init = start.copy()
+    init[:, :3] += [[0.004, -0.003, 0.004], [-0.003, 0.004, -0.004]]
+    dev = DeviceParticleTracker(s_dev, prm, seed=99)
+    host = ParticleTracker(s_host, 2, prm, seed=99, counter_noise=True)
+    dev.initialize(init)
+    host.initialize(init)
+    assert dev.n == host.n == 300
+    est_d, est_h = [], []
+    for img in frames:
+        est_d.append(dev.track(img))
+        est_h.append(host.track(img))
+    est_d, est_h, truth = np.array(est_d), np.array(est_h), np.array(truth)
+    # same noise, same sensor arithmetic: the two tracks agree far below the tracking error
+    assert np.max(np.abs(est_d[:4] - est_h[:4])) < 1e-6, np.max(np.abs(est_d - est_h), axis=(1, 2))
+    assert np.max(np.abs(est_d - est_h)) < 5e-4, np.max(np.abs(est_d - est_h), axis=(1, 2))
+    err = np.linalg.norm(est_d[:, :, :3] - truth, axis=2)
+    assert err[-6:].max() < 0.004, err
+    assert dev.resample_count >= 1 and abs(dev.resample_count - host.resample_count) <= 2
+    assert s_dev.n_slots == 300
