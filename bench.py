@@ -50,7 +50,8 @@ def describe(w, n_gpus):
                         % (CONFIG_ID, w["n"], w["cols"], w["rows"], w["mesh"], w["tris"]),
             "particles_per_gpu": w["n"], "particles_total": w["n"] * n_gpus,
             "resolution": [w["cols"], w["rows"]], "triangles": w["tris"],
-            "occlusion_mode": "dense-eager", "parallelism": "particles sharded x%d" % n_gpus,
+            "occlusion_mode": "dense", "parallelism": "particles sharded x%d" % n_gpus,
+            "parents": "systematic resampling of Gamma(0.5) weights on every step (about 50 % distinct parents)",
             "l2_policy": "inputs larger than L2 (%.2f GB occlusion state read + written per step)"
                          % (2 * w["n"] * w["rows"] * w["cols"] * 4 / 1e9)}
 

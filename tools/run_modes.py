@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--n", type=int, default=0)
-    ap.add_argument("--parents", default="resampled", choices=["resampled", "identity"],
+    ap.add_argument("--parents", default="resampled", choices=["resampled", "identity", "few"],
                     help="parent pattern of the update calls: systematic resampling every frame, or none")
     a = ap.parse_args()
     import torch
@@ -38,8 +38,15 @@ def main():
     gt = synth.ground_truth_poses(len(w["V"]), rng)
     frames = [synth.make_frame(sensor.render, gt, rows, cols, rng) for _ in range(2)]
     poses = [synth.particle_poses(gt, n, rng) for _ in range(2)]
-    parents = [bench.resampled_parents(n, rng) if a.parents == "resampled" else np.arange(n, dtype=np.int32)
-               for _ in range(2)]
+    def make_parents():
+        if a.parents == "resampled":
+            return bench.resampled_parents(n, rng)
+        if a.parents == "identity":
+            return np.arange(n, dtype=np.int32)
+        # "few": what a peaked likelihood does to systematic resampling -- a handful of distinct parents
+        return np.sort(rng.choice(rng.choice(n, 8, replace=False), n)).astype(np.int32)
+
+    parents = [make_parents() for _ in range(2)]
     dev = torch.device("cuda", 0)
     d_frames = [torch.from_numpy(f).to(dev) for f in frames]
     d_poses = [torch.from_numpy(p).to(dev) for p in poses]
