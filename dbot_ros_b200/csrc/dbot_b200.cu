@@ -383,8 +383,11 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
 {
     const int ww = col1 - col0 + 1;
     const uint32_t tile_s = smem_u32(s_wt);
-    __shared__ uint32_t s_dummy[DBOT_CW][32];
-    const uint32_t dummy_s = smem_u32(&s_dummy[threadIdx.x >> 5][lane]);
+    /* dummy words: 8 consecutive ones per lane (the column offset stays an immediate of the atomic),
+     * staggered so that the 32 lanes of a warp hit 32 different banks at every column; one set serves
+     * all warps -- a warp instruction owns the shared-memory pipe while it executes */
+    __shared__ uint32_t s_dummy[8 * 31 + 7 + 8];
+    const uint32_t dummy_s = smem_u32(&s_dummy[8 * lane + (lane >> 2)]);
     for (;;)
     {
         int base = 0;
@@ -497,14 +500,16 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
                  * slots than the atomics it saves; so every covered pixel sends its inverse depth
                  * to the tile's max, and every pixel outside the triangle sends it to a per-lane
                  * dummy word instead (own bank: no conflict, no branch). */
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc)
-                {
-                    const int eor = (x0 + cc * o_e0c) | (x1 + cc * o_e1c) | (x2 + cc * o_e2c);
-                    const uint32_t bits = dbot_f2u(fminf(fmaxf(dbot_fmaf(o_m0, fc[cc], wr), o_wlo), o_whi));
-                    const uint32_t a = eor >= 0 ? trow + 4u * cc : dummy_s;
-                    asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(a), "r"(bits) : "memory");
-                }
+#define DBOT_SWEEP_PIXEL(cc)                                                                          \
+    {                                                                                                  \
+        const int eor = (x0 + (cc) * o_e0c) | (x1 + (cc) * o_e1c) | (x2 + (cc) * o_e2c);              \
+        const uint32_t bits = dbot_f2u(fminf(fmaxf(dbot_fmaf(o_m0, fc[cc], wr), o_wlo), o_whi));       \
+        const uint32_t a = eor >= 0 ? trow : dummy_s;                                                   \
+        asm volatile("red.shared.max.u32 [%0+%2], %1;" ::"r"(a), "r"(bits), "n"(4 * (cc)) : "memory"); \
+    }
+                DBOT_SWEEP_PIXEL(0) DBOT_SWEEP_PIXEL(1) DBOT_SWEEP_PIXEL(2) DBOT_SWEEP_PIXEL(3)
+                DBOT_SWEEP_PIXEL(4) DBOT_SWEEP_PIXEL(5) DBOT_SWEEP_PIXEL(6) DBOT_SWEEP_PIXEL(7)
+#undef DBOT_SWEEP_PIXEL
                 x0 += o_e0r; x1 += o_e1r; x2 += o_e2r;
                 fr = dbot_add(fr, 1.0f);
                 trow += 4u * (uint32_t)ww;
