@@ -733,6 +733,14 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
         const float* occ_in = p.pool + (size_t)pl.x * p.slot_stride;
         float* occ_out = (MODE == DBOT_MODE_UPDATE) ? p.pool + (size_t)pl.y * p.slot_stride : nullptr;
 
+#ifdef DBOT_DBG_TIMELINE
+        long long tl[8];
+        int tli = 0;
+#define DBOT_TL() do { if (tli < 8) tl[tli++] = clock64(); } while (0)
+#else
+#define DBOT_TL() do { } while (0)
+#endif
+        DBOT_TL();
         /* ---- pass 1: transform every chunk, collect the screen window of the particle ---- */
         if (tid == 0)
         {
@@ -768,6 +776,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
             r0 = max(dbot_ceil_subpix(s_bb[2]), 0);
             r1 = min(dbot_floor_subpix(s_bb[3]), p.rows - 1);
         }
+        DBOT_TL(); /* transform + window done */
         const bool have_window = (c0 <= c1) && (r0 <= r1);
         const int ww = c1 - c0 + 1;
         float acc = 0.0f;
@@ -808,8 +817,10 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                     stage_chunk(0); /* resident after the first particle */
                     if (tid == 0) s_batch = 0;
                     compute_sync();
+                    DBOT_TL(); /* tile cleared */
                     dbot_raster_chunk(s_tri, p.chunks[0].n_tris, s_v4, s_Y, p.K, s_wt, s_owner_all[warp],
                                       &s_batch, rb0, rb1, c0, c1, lane);
+                    DBOT_TL(); /* this warp's raster done */
                 }
                 else
                 {
@@ -891,6 +902,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
             }
         }
         if (MODE == DBOT_MODE_UPDATE && !copied) await_slot();
+        DBOT_TL(); /* this warp's mixture done */
 
         /* ---- one log-weight per particle: fixed shuffle tree, double across warps ---- */
         if (MODE != DBOT_MODE_RENDER)
@@ -906,6 +918,14 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
 #pragma unroll
                 for (int w = 0; w < DBOT_CW; ++w) s += s_red[w];
                 p.out[i] = s;
+#ifdef DBOT_DBG_TIMELINE
+                DBOT_TL();
+                if (blockIdx.x == 3 && k >= 3 * (int)gridDim.x && k < 5 * (int)gridDim.x)
+                    printf("mode %d particle %d cycles: transform+window %lld clear %lld raster(w0) %lld "
+                           "mixture(w0, incl. wait for other warps' raster) %lld reduce %lld total %lld\n",
+                           MODE, i, tl[1] - tl[0], tl[2] - tl[1], tl[3] - tl[2], tl[4] - tl[3], tl[5] - tl[4],
+                           tl[5] - tl[0]);
+#endif
                 if (MODE == DBOT_MODE_UPDATE)
                 {
                     p.indices[i] = i;
