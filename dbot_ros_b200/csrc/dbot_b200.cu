@@ -6,16 +6,20 @@
  * selects with use_gpu:true (ref:config/particle_tracker.yaml:3,
  * ref:source/dbot_ros/tracker/particle_tracker_node.cpp:164-203).  Nothing here is derived
  * from that code: one persistent CTA per SM walks the particles; per particle it
- *   1. stages the mesh chunk (vertices + uint16 triangle indices) in shared memory with
- *      TMA bulk copies (cp.async.bulk + mbarrier) -- resident across particles when the
- *      mesh is a single chunk,
+ *   1. stages the mesh chunk's uint16 triangle list in shared memory with a TMA bulk copy
+ *      (cp.async.bulk + mbarrier) -- resident across particles when the mesh is a single chunk,
  *   2. transforms + projects + snaps the vertices (shared memory SoA),
- *   3. rasterises all triangles into a shared-memory z tile covering the particle's
- *      screen window with exact integer edge functions and atomicMin on the depth bits,
+ *   3. rasterises all triangles into a shared-memory tile of inverse depths covering the
+ *      particle's screen window: exact integer edge functions, branch-free shared-memory max on
+ *      the bits of the positive float,
  *   4. evaluates the per-pixel visible/occluded mixture against the per-frame observation
- *      table and the parent's occlusion image, and on update streams the propagated /
- *      posterior occlusion image of the child slot,
+ *      table and the parent's stored occlusion image, and on update writes the posterior of the
+ *      covered pixels into the child's slot,
  *   5. reduces to one double log-weight with a fixed shuffle tree (deterministic).
+ * The occlusion state lives in a pool of physical slots: propagation is composed lazily into two
+ * numbers, the last child of every parent adopts the parent's slot in place and only the other
+ * children get a copy, streamed by four extra warps while the compute warps rasterise
+ * (dbot_plan_update_kernel).  dbot_filter.cuh adds the device-resident filter step around it.
  * There is no CPU fallback in this library.
  */
 #include "../../include/dbot_b200.h"
