@@ -20,6 +20,7 @@
  * that need int64 edge functions and the ones whose box dwarfs the batch are instead walked by
  * the whole warp, 8 x 4 pixels per step with explicit bounds.                                  */
 #define DBOT_OWNER_CAP 512 /* blocks per batch: 32 lanes x at most 16 blocks each */
+#define DBOT_BIG_BLOCKS 16 /* a triangle with more blocks than a lane's share of the table: whole-warp walk */
 
 __device__ __forceinline__ void dbot_zmax(uint32_t* p, uint32_t v)
 {
@@ -60,11 +61,8 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
         __syncwarp();
         const int bw = ok ? (s.cmax - s.cmin + 8) >> 3 : 0; /* blocks of 8 columns */
         const int bh = ok ? (s.rmax - s.rmin + 4) >> 2 : 0; /* blocks of 4 rows */
-        int tot = bw * bh;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(DBOT_FULL, tot, off);
-        /* whole-warp walk: int64 edge functions, window-cut boxes, > 4 x the batch mean */
-        const bool big = ok && (!s.small || s.clipped || bw * bh > min(16, max(8, tot >> 3)));
+        /* whole-warp walk: int64 edge functions, window-cut boxes, more blocks than a lane's share of the owner table */
+        const bool big = ok && (!s.small || s.clipped || bw * bh > DBOT_BIG_BLOCKS);
         const bool mine = ok && !big;
         const int nb = mine ? bw * bh : 0;
 
