@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 from dbot_ros_b200 import CameraData, ObjectModel, Parameters, RbSensorBuilder, synth  # noqa: E402
 
-METRIC = "particle_likelihoods_per_sec"
+METRIC = "particle-likelihoods/sec"  # BASELINE.json: "particle-likelihoods/sec & FPS @640x480, 5k-tri mesh, ..." (FPS is the line's "fps" key)
 UNIT = "particle-likelihoods/s"
 CONFIG_ID = 2            # BASELINE.json configs[1]: 1000 particles, 640x480, single 5k-tri mesh
 N_FRAMES = 4             # distinct synthetic frames / pose sets cycled through the steps
