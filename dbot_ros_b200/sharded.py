@@ -190,18 +190,17 @@ class ShardedRbSensor(RbSensor):
         """global parent slots of this rank's particles -> local slot numbers (after migrate())"""
         lo, hi = shard_bounds(n, self.world, self.rank)
         parents = np.asarray(indices[lo:hi], dtype=np.int64)
-        if np.any(np.asarray(indices) < 0) or np.any(np.asarray(indices) >= self.n_slots):
-            raise IndexError("loglikes: parent slot out of range (have %d)" % self.n_slots)
         if self.n_slots == 1:
             return lo, hi, np.zeros(hi - lo, dtype=np.int32)
         plo, phi = shard_bounds(self.n_slots, self.world, self.rank)
-        out = np.empty(hi - lo, dtype=np.int32)
-        for k, s in enumerate(parents):
-            out[k] = s - plo if plo <= s < phi else self._imported_local[int(s)]
+        out = (parents - plo).astype(np.int32)
+        for k in np.nonzero((parents < plo) | (parents >= phi))[0]:   # migrated parents (rare)
+            out[k] = self._imported_local[int(parents[k])]
         return lo, hi, out
 
     def all_gather(self, local_values, n):
-        """all-gather of ragged shards: pad to the largest shard, one collective, unpad"""
+        """all-gather of ragged shards: pad to the largest shard, one collective, unpad.  Buffers are
+        kept between calls (page-locked on the host when the collective runs on a GPU)."""
         import torch
         import torch.distributed as dist
 
@@ -209,13 +208,22 @@ class ShardedRbSensor(RbSensor):
         width = max(counts) if counts else 0
         if width == 0:
             return np.zeros(0, dtype=np.float64)
-        send = torch.zeros(width, dtype=torch.float64)
-        send[: len(local_values)] = torch.from_numpy(np.ascontiguousarray(local_values, dtype=np.float64))
-        send = send.to(self.device)
         if self._buf is None or self._buf.numel() != width * self.world:
+            cuda = self.device.type == "cuda"
+            self._send_host = torch.zeros(width, dtype=torch.float64, pin_memory=cuda)
+            self._recv_host = torch.zeros(width * self.world, dtype=torch.float64, pin_memory=cuda)
+            self._send = self._send_host.to(self.device) if cuda else self._send_host
             self._buf = torch.empty(width * self.world, dtype=torch.float64, device=self.device)
-        dist.all_gather_into_tensor(self._buf, send, group=self.group)
-        got = self._buf.cpu().numpy().reshape(self.world, width)
+        self._send_host[: len(local_values)] = torch.from_numpy(np.ascontiguousarray(local_values, dtype=np.float64))
+        if self.device.type == "cuda":
+            self._send.copy_(self._send_host, non_blocking=True)
+            dist.all_gather_into_tensor(self._buf, self._send, group=self.group)
+            self._recv_host.copy_(self._buf, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            got = self._recv_host.numpy().reshape(self.world, width)
+        else:
+            dist.all_gather_into_tensor(self._buf, self._send, group=self.group)
+            got = self._buf.numpy().reshape(self.world, width)
         return np.concatenate([got[r, : counts[r]] for r in range(self.world)])
 
     def loglikes_poses(self, poses, indices, update=False):
