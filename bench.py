@@ -143,6 +143,9 @@ class ClockSampler:
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+_HOST_THREADS = None
+
+
 def cpu_oracle_rate(w, frames, poses, sample, reps, threads=None, min_seconds=0.0, max_reps=None):
     """oracle on the host cores: set_observation + loglikes(update) on `sample` particles per step;
     runs `reps` steps, then keeps going until `min_seconds` of CPU work have been timed"""
@@ -150,7 +153,10 @@ def cpu_oracle_rate(w, frames, poses, sample, reps, threads=None, min_seconds=0.
     import oracle_lib
 
     orc = oracle_lib.Oracle(w["rows"], w["cols"], w["K"], w["V"], w["T"], synth.default_parameters())
-    cores = oracle_lib.oracle_lib().oracle_get_max_threads() if threads is None else threads
+    global _HOST_THREADS
+    if _HOST_THREADS is None:  # OpenMP's default team size, read before anything narrows it
+        _HOST_THREADS = oracle_lib.oracle_lib().oracle_get_max_threads()
+    cores = _HOST_THREADS if threads is None else threads
     oracle_lib.oracle_lib().oracle_set_num_threads(cores)
     idx = np.zeros(sample, dtype=np.int32)
     orc.set_observation(frames[0])
@@ -399,6 +405,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = min(n, 250)
         rate, cores, sec, reps = cpu_oracle_rate(w, frames, poses, sample, reps=4, min_seconds=12.0, max_reps=400)
+        # the reference's own loglikes is a serial loop over the particles: one thread, small sample
+        rate1, _, sec1, reps1 = cpu_oracle_rate(w, frames, poses, 32, reps=3, threads=1)
+        line["cpu_baseline_single_thread"] = {"value": rate1, "unit": UNIT, "cores": 1, "kind": "port",
+                                              "sample": "32 particles per step, %d steps" % reps1}
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "%d of the %d particles per step, %d steps (%.1f s of CPU work), same "
                                           "frames, OpenMP over particles" % (sample, n, reps, sec * reps)}
