@@ -12,8 +12,9 @@ particles (ref:source/dbot_ros/object_tracker_ros.hpp:49 -> dbot filter, SURVEY.
           log-weights out; H2D/D2H inside the timed region).
   roofline  the fused particle kernel (update): algorithmic bytes = 8*P per particle (read the
           parent's fp32 occlusion image, write the child's), launch duration from CUDA events.
-  cpu_baseline / --impl reference   the CPU oracle (oracle/, OpenMP over particles, all host
-          cores) on a bounded particle sample of the same frames.
+  cpu_baseline / --impl reference   the CPU oracle (oracle/, lazily propagated occlusion state as in
+          dbot's CPU model, OpenMP over particles, all host cores) on a bounded particle sample of
+          the same frames.
 """
 import argparse
 import json
@@ -152,7 +153,9 @@ def cpu_oracle_rate(w, frames, poses, sample, reps, threads=None, min_seconds=0.
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
 
-    orc = oracle_lib.Oracle(w["rows"], w["cols"], w["K"], w["V"], w["T"], synth.default_parameters())
+    # eager=0: per-pixel time stamps and propagation on demand, the way dbot's CPU KinectImageModel keeps
+    # its occlusion state (2.7x faster on the CPU than propagating whole images as the GPU evaluators do)
+    orc = oracle_lib.Oracle(w["rows"], w["cols"], w["K"], w["V"], w["T"], synth.default_parameters(), eager=0)
     global _HOST_THREADS
     if _HOST_THREADS is None:  # OpenMP's default team size, read before anything narrows it
         _HOST_THREADS = oracle_lib.oracle_lib().oracle_get_max_threads()
