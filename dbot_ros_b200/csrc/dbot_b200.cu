@@ -41,14 +41,18 @@
 #define DBOT_CT (DBOT_CW * 32)     /* compute threads */
 #define DBOT_SW 4                  /* streaming warps per CTA (update launches only) */
 #define DBOT_ST (DBOT_SW * 32)
+#ifndef DBOT_STREAM_UNROLL
 #define DBOT_STREAM_UNROLL 4       /* 256-bit loads in flight per streaming thread */
+#endif
 /* update launches start every thread with 96 registers (640 threads); the streaming warp group
  * hands most of its share to the four compute warp groups (setmaxnreg) */
 #ifndef DBOT_PREFETCH_AHEAD
 #define DBOT_PREFETCH_AHEAD 8      /* chunks of DBOT_ST x DBOT_STREAM_UNROLL x 32 B (16 KB) */
 #endif
+#ifndef DBOT_STREAM_REGS
 #define DBOT_STREAM_REGS 56
 #define DBOT_COMPUTE_REGS 104
+#endif
 #define DBOT_CHUNK_MAX_VERTS 3072
 #define DBOT_CHUNK_MAX_TRIS 6144
 #define DBOT_FULL 0xffffffffu
