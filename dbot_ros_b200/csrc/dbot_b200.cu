@@ -658,7 +658,15 @@ extern "C" int dbot_b200_loglikes(dbot_b200_sensor* s, const float* poses, int32
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(s->h_out, s->d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost,
                              s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->h_err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (*s->h_err)
+    {
+        const int code = *s->h_err;
+        cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream);
+        return code == 2 ? fail(-10, "loglikes: the occlusion-slot pool is exhausted (too many imported slots)")
+                         : fail(-7, "loglikes: a parent index was not a valid occlusion slot");
+    }
     memcpy(out_loglikes, s->h_out, (size_t)n * sizeof(double));
     if (update)
         for (int i = 0; i < n; ++i) indices[i] = i;
