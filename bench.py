@@ -371,6 +371,7 @@ def main():
     clocks.__exit__()
     k_ms, k_cnt = prof["update"]
     o_ms, o_cnt = prof["observation"]
+    p_ms, p_cnt = prof["plan"]
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -394,8 +395,9 @@ def main():
                 "dram__bytes_write.sum, one launch)" if traffic else None,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "avg_launch_ms": avg_ms, "launches_timed": k_cnt,
-                "kernel_share_of_step": k_ms / max(k_ms + o_ms, 1e-9),
-                "observation_kernel_avg_ms": o_ms / max(o_cnt, 1)}
+                "kernel_share_of_step": k_ms / max(k_ms + o_ms + p_ms, 1e-9),
+                "observation_kernel_avg_ms": o_ms / max(o_cnt, 1),
+                "plan_kernel_avg_ms": p_ms / max(p_cnt, 1)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

@@ -10,7 +10,7 @@ import numpy as np
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdbot_b200.so")
 MAX_OBJECTS = 8
-KERNEL_NAMES = ("observation", "loglikes", "update", "render")
+KERNEL_NAMES = ("observation", "loglikes", "update", "render", "plan")
 
 
 class DbotB200Error(RuntimeError):

@@ -605,11 +605,12 @@ static int launch_particles(dbot_b200_sensor* s, const float* d_poses, int32_t* 
     kp.post_inv_a = (float)(1.0 / A);
     if (update)
     {
+        prof_begin(s);
         dbot_plan_update_kernel<<<1, DBOT_PLAN_THREADS, 0, s->stream>>>(
             d_indices, n, s->n_slots, s->d_loc[s->cur], s->d_loc[s->cur ^ 1], s->d_free, s->d_free_count,
             s->d_cnt, s->d_last, s->d_pending, s->d_order, s->d_plan, s->d_err);
-        s->launches++;
         CUDA_TRY(cudaGetLastError());
+        prof_end(s, DBOT_B200_KERNEL_PLAN);
     }
     const int grid = std::min(n, s->grid_max);
     prof_begin(s);

@@ -146,7 +146,8 @@ int dbot_b200_timer_end(dbot_b200_sensor* s, float* out_ms);
 #define DBOT_B200_KERNEL_LOGLIKES 1    /* raster + likelihood, update == 0       */
 #define DBOT_B200_KERNEL_UPDATE 2      /* raster + likelihood + occlusion stream */
 #define DBOT_B200_KERNEL_RENDER 3
-#define DBOT_B200_KERNEL_COUNT 4
+#define DBOT_B200_KERNEL_PLAN 4        /* update planning (slot adoption / copies)  */
+#define DBOT_B200_KERNEL_COUNT 5
 int dbot_b200_profile_enable(dbot_b200_sensor* s, int32_t on);
 /* sums since the last call; arrays of DBOT_B200_KERNEL_COUNT entries */
 int dbot_b200_profile_read(dbot_b200_sensor* s, float* out_ms, int64_t* out_launches);
