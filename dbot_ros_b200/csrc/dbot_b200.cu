@@ -364,12 +364,16 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
         return fail(-9, "image too wide for the shared-memory depth tile (cols=%d)", kp.cols);
     s->smem_bytes = smem_max;
     kp.wcap = ((uint32_t)(smem_max - (int)off) / 16u) * 4u; /* pixels, multiple of 4 */
-    CUDA_TRY(cudaFuncSetAttribute(dbot_particle_kernel<DBOT_MODE_EVAL>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
-    CUDA_TRY(cudaFuncSetAttribute(dbot_particle_kernel<DBOT_MODE_UPDATE>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
-    CUDA_TRY(cudaFuncSetAttribute(dbot_particle_kernel<DBOT_MODE_RENDER>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
+    {
+        const void* kernels[] = {(const void*)dbot_particle_kernel<DBOT_MODE_EVAL, false>,
+                                 (const void*)dbot_particle_kernel<DBOT_MODE_EVAL, true>,
+                                 (const void*)dbot_particle_kernel<DBOT_MODE_UPDATE, false>,
+                                 (const void*)dbot_particle_kernel<DBOT_MODE_UPDATE, true>,
+                                 (const void*)dbot_particle_kernel<DBOT_MODE_RENDER, false>,
+                                 (const void*)dbot_particle_kernel<DBOT_MODE_RENDER, true>};
+        for (const void* k : kernels)
+            CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
+    }
     s->grid_max = s->num_sms; /* one persistent CTA per SM (launch bounds: 1 CTA/SM) */
 
     /* buffers */
@@ -618,11 +622,18 @@ static int launch_particles(dbot_b200_sensor* s, const float* d_poses, int32_t* 
     {
         /* adopting children spin on their siblings' copies: every CTA must be resident */
         void* args[] = {(void*)&kp};
-        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)dbot_particle_kernel<DBOT_MODE_UPDATE>, dim3(grid),
+        const void* kern = kp.n_chunks > 1 ? (const void*)dbot_particle_kernel<DBOT_MODE_UPDATE, true>
+                                           : (const void*)dbot_particle_kernel<DBOT_MODE_UPDATE, false>;
+        CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(grid),
                                              dim3(DBOT_CT + DBOT_ST), args, (size_t)s->smem_bytes, s->stream));
     }
     else
-        dbot_particle_kernel<DBOT_MODE_EVAL><<<grid, DBOT_CT, s->smem_bytes, s->stream>>>(kp);
+    {
+        if (kp.n_chunks > 1)
+            dbot_particle_kernel<DBOT_MODE_EVAL, true><<<grid, DBOT_CT, s->smem_bytes, s->stream>>>(kp);
+        else
+            dbot_particle_kernel<DBOT_MODE_EVAL, false><<<grid, DBOT_CT, s->smem_bytes, s->stream>>>(kp);
+    }
     CUDA_TRY(cudaGetLastError());
     prof_end(s, update ? DBOT_B200_KERNEL_UPDATE : DBOT_B200_KERNEL_LOGLIKES);
     if (update)
@@ -725,7 +736,10 @@ extern "C" int dbot_b200_render(dbot_b200_sensor* s, const float* pose, float* o
         kp.depth_out = s->d_depth;
         kp.err_flag = s->d_err;
         prof_begin(s);
-        dbot_particle_kernel<DBOT_MODE_RENDER><<<1, DBOT_CT, s->smem_bytes, s->stream>>>(kp);
+        if (kp.n_chunks > 1)
+            dbot_particle_kernel<DBOT_MODE_RENDER, true><<<1, DBOT_CT, s->smem_bytes, s->stream>>>(kp);
+        else
+            dbot_particle_kernel<DBOT_MODE_RENDER, false><<<1, DBOT_CT, s->smem_bytes, s->stream>>>(kp);
         e = cudaGetLastError();
         prof_end(s, DBOT_B200_KERNEL_RENDER);
     }

@@ -19,6 +19,7 @@
  * box mask is needed -- unless the box was cut by the raster window; those triangles, the ones
  * that need int64 edge functions and the ones whose box dwarfs the batch are instead walked by
  * the whole warp, 8 x 4 pixels per step with explicit bounds.                                  */
+#define DBOT_BOX_CHUNKS 32 /* chunks beyond this many are never culled against a tile */
 #define DBOT_OWNER_CAP 512 /* blocks per batch: 32 lanes x at most 16 blocks each */
 #define DBOT_BIG_BLOCKS 16 /* a triangle with more blocks than a lane's share of the table: whole-warp walk */
 
@@ -205,13 +206,14 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
  * stream the parent's propagated occlusion image into the child's slot while the compute warps
  * transform and rasterise the same particle; the compute warps then overwrite the covered
  * pixels with the posterior.  Hand-off through two named barriers (copied / consumed). */
-template <int MODE>
+template <int MODE, bool MULTI> /* MULTI: the mesh is split into several chunks (big or multi-object) */
 __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST : 0), 1)
     dbot_particle_kernel(const __grid_constant__ dbot_kparams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_bar;      /* TMA mesh staging */
     __shared__ int s_bb[4];
+    __shared__ int s_cbb[DBOT_BOX_CHUNKS][4]; /* snapped box of each mesh chunk (multi-chunk meshes) */
     __shared__ int s_batch;                      /* next triangle batch of the current raster pass */
     __shared__ unsigned char s_owner_all[DBOT_CW][DBOT_OWNER_CAP]; /* block -> owning lane, per warp */
     __shared__ double s_red[DBOT_CW];
@@ -394,13 +396,32 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
         {
             s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN;
         }
+        if (MULTI && tid < 4 * DBOT_BOX_CHUNKS) s_cbb[tid >> 2][tid & 3] = (tid & 1) ? INT_MIN : INT_MAX;
         compute_sync(); /* also fences the previous particle's use of shared memory */
         int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
         for (int c = 0; c < p.n_chunks; ++c)
         {
-            if (c > 0) compute_sync(); /* multi-chunk: only the bounding box survives this pass */
+            if (c > 0) compute_sync(); /* multi-chunk: only the bounding boxes survive this pass */
             const dbot_chunk ch = p.chunks[c];
-            transform_chunk(ch, pose + 12 * ch.obj, mnx, mxx, mny, mxy);
+            int a0 = INT_MAX, a1 = INT_MIN, a2 = INT_MAX, a3 = INT_MIN;
+            transform_chunk(ch, pose + 12 * ch.obj, a0, a1, a2, a3);
+            mnx = min(mnx, a0); mxx = max(mxx, a1); mny = min(mny, a2); mxy = max(mxy, a3);
+            if (MULTI && c < DBOT_BOX_CHUNKS)
+            {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1)
+                {
+                    a0 = min(a0, __shfl_xor_sync(DBOT_FULL, a0, off));
+                    a1 = max(a1, __shfl_xor_sync(DBOT_FULL, a1, off));
+                    a2 = min(a2, __shfl_xor_sync(DBOT_FULL, a2, off));
+                    a3 = max(a3, __shfl_xor_sync(DBOT_FULL, a3, off));
+                }
+                if (lane == 0)
+                {
+                    atomicMin(&s_cbb[c][0], a0); atomicMax(&s_cbb[c][1], a1);
+                    atomicMin(&s_cbb[c][2], a2); atomicMax(&s_cbb[c][3], a3);
+                }
+            }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1)
@@ -449,10 +470,21 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
 
         if (have_window)
         {
-            const int band_rows = max(1, (int)(p.wcap / (uint32_t)ww));
-            for (int rb0 = r0; rb0 <= r1; rb0 += band_rows)
+            /* The window is cut into tiles that fit the shared-memory z tile: row bands of the full
+             * width, or -- when the window is wider than tall, e.g. several objects side by side --
+             * column bands of the full height, so that a tile meets as few mesh chunks as possible. */
+            const int wc0 = c0, wc1 = c1, wh = r1 - r0 + 1;
+            int tile_rows = max(1, (int)(p.wcap / (uint32_t)ww)), tile_cols = ww;
+            if (MULTI && tile_rows < wh && ww > wh && (uint32_t)wh * 32u <= p.wcap)
             {
-                const int rb1 = min(rb0 + band_rows - 1, r1);
+                tile_rows = wh;
+                tile_cols = (int)(p.wcap / (uint32_t)wh);
+            }
+            for (int rb0 = r0; rb0 <= r1; rb0 += tile_rows)
+            for (int cb0 = wc0; cb0 <= wc1; cb0 += tile_cols)
+            {
+                const int rb1 = min(rb0 + tile_rows - 1, r1);
+                const int c0 = cb0, c1 = min(cb0 + tile_cols - 1, wc1), ww = c1 - c0 + 1; /* this tile */
                 const int npx = (rb1 - rb0 + 1) * ww;
                 compute_sync(); /* previous band's readers of the tile are done */
                 {
@@ -460,7 +492,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                     const int n4 = (npx + 3) >> 2; /* wcap is a multiple of 4 */
                     for (int q = tid; q < n4; q += DBOT_CT) w4[q] = make_uint4(0u, 0u, 0u, 0u);
                 }
-                if (p.n_chunks == 1)
+                if (!MULTI)
                 {
                     stage_chunk(0); /* resident after the first particle */
                     if (tid == 0) s_batch = 0;
@@ -474,6 +506,13 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                 {
                     for (int c = 0; c < p.n_chunks; ++c)
                     {
+                        if (c < DBOT_BOX_CHUNKS) /* a chunk whose box misses the tile is not even staged */
+                        {
+                            const int b0 = s_cbb[c][0], b1 = s_cbb[c][1], b2 = s_cbb[c][2], b3 = s_cbb[c][3];
+                            if (b0 > b1 || dbot_ceil_subpix(b0) > c1 || dbot_floor_subpix(b1) < c0 ||
+                                dbot_ceil_subpix(b2) > rb1 || dbot_floor_subpix(b3) < rb0)
+                                continue;
+                        }
                         stage_chunk(c); /* leading barrier orders tile init / previous raster */
                         const dbot_chunk ch = p.chunks[c];
                         int d0 = INT_MAX, d1 = INT_MIN, d2 = INT_MAX, d3 = INT_MIN;
