@@ -157,8 +157,10 @@ def cpu_oracle_rate(w, frames, poses, sample, reps, threads=None, min_seconds=0.
     # its occlusion state (2.7x faster on the CPU than propagating whole images as the GPU evaluators do)
     orc = oracle_lib.Oracle(w["rows"], w["cols"], w["K"], w["V"], w["T"], synth.default_parameters(), eager=0)
     global _HOST_THREADS
-    if _HOST_THREADS is None:  # OpenMP's default team size, read before anything narrows it
-        _HOST_THREADS = oracle_lib.oracle_lib().oracle_get_max_threads()
+    if _HOST_THREADS is None:
+        # every core this process may run on -- not OpenMP's default, which torchrun pins to 1 by
+        # exporting OMP_NUM_THREADS=1 to its workers
+        _HOST_THREADS = max(len(os.sched_getaffinity(0)), oracle_lib.oracle_lib().oracle_get_max_threads())
     cores = _HOST_THREADS if threads is None else threads
     oracle_lib.oracle_lib().oracle_set_num_threads(cores)
     idx = np.zeros(sample, dtype=np.int32)
