@@ -676,6 +676,7 @@ extern "C" int dbot_b200_loglikes(dbot_b200_sensor* s, const float* poses, int32
     {
         const int code = *s->h_err;
         cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream);
+        if (code == 3) return fail(-11, "loglikes: an adopting particle timed out waiting for its siblings' copies");
         return code == 2 ? fail(-10, "loglikes: the occlusion-slot pool is exhausted (too many imported slots)")
                          : fail(-7, "loglikes: a parent index was not a valid occlusion slot");
     }
@@ -710,6 +711,7 @@ extern "C" int dbot_b200_synchronize(dbot_b200_sensor* s)
         const int code = *s->h_err;
         cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream);
         if (code == 2) return fail(-10, "the occlusion-slot pool is exhausted (too many imported slots)");
+        if (code == 3) return fail(-11, "an adopting particle timed out waiting for its siblings' copies");
         return fail(-7, "loglikes_device: an index was not a valid occlusion slot");
     }
     return 0;

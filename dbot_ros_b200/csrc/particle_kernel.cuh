@@ -460,7 +460,18 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
             {
                 if (tid == 0)
                 {
-                    while (atomicAdd(p.pending + pl.z, 0) > 0) __nanosleep(200);
+                    /* siblings never wait for anything, so this ends; the bound (about a second) only
+                     * turns a scheduling accident into an error code instead of a hung GPU */
+                    int spins = 0;
+                    while (atomicAdd(p.pending + pl.z, 0) > 0)
+                    {
+                        __nanosleep(200);
+                        if (++spins > (1 << 22))
+                        {
+                            atomicExch(p.err_flag, 3);
+                            break;
+                        }
+                    }
                     __threadfence();
                 }
                 compute_sync();
