@@ -409,6 +409,29 @@ def main():
                     "fps": args.steps / e2e_s},
             "gpu_launches": gpu_launches, "clocks": clocks.summary(), "roofline": roofline}
 
+    if rank == 0 and world == 1:
+        # the same frames through the device-resident filter step (dbot_b200_filter_*): frame in, pose out
+        try:
+            from dbot_ros_b200.tracker import DeviceParticleTracker, TrackerParameters
+
+            R0, t0 = gt[0]
+            from dbot_ros_b200.tracker import rotation_vector
+
+            trk = DeviceParticleTracker(sensor, TrackerParameters(evaluation_count=n), seed=1)
+            trk.initialize([np.concatenate([t0, rotation_vector(R0)])])
+            for k in range(3):
+                trk.track(frames[k % N_FRAMES])
+            t1 = time.perf_counter()
+            for k in range(args.steps):
+                est = trk.track(frames[k % N_FRAMES])
+            dt_f = (time.perf_counter() - t1) / args.steps
+            line["filter"] = {"frames_per_s": 1.0 / dt_f, "particle_likelihoods_per_s": n / dt_f,
+                              "position_error_mm": 1e3 * float(np.linalg.norm(est[0, :3] - t0)),
+                              "what": "dbot_b200_filter_track: host depth frame in, integrated pose out, "
+                                      "filter state resident in HBM"}
+            trk.close()
+        except Exception as e:  # the bench line does not depend on it
+            line["filter"] = {"error": str(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = min(n, 250)
         rate, cores, sec, reps = cpu_oracle_rate(w, frames, poses, sample, reps=4, min_seconds=12.0, max_reps=400)
