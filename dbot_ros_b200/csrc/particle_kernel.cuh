@@ -17,8 +17,8 @@
  * inverse depth, address select, shared-memory max on the bits of the positive float).
  * Pixels of a block outside the triangle's own box fail the edge test by themselves, so no
  * box mask is needed -- unless the box was cut by the raster window; those triangles, the ones
- * that need int64 edge functions and the ones whose box dwarfs the batch are instead walked by
- * the whole warp, 8 x 4 pixels per step with explicit bounds.                                  */
+ * that need int64 edge functions and the ones with more than DBOT_BIG_BLOCKS blocks are instead
+ * walked by the whole warp, 8 x 4 pixels per step with explicit bounds.                        */
 #define DBOT_BOX_CHUNKS 32 /* chunks beyond this many are never culled against a tile */
 #define DBOT_OWNER_CAP 512 /* blocks per batch: 32 lanes x at most 16 blocks each */
 #define DBOT_BIG_BLOCKS 16 /* a triangle with more blocks than a lane's share of the table: whole-warp walk */
@@ -201,11 +201,13 @@ __device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* K2: fused transform + raster + likelihood (+ occlusion stream) kernel.
+/* K2: fused transform + raster + likelihood (+ occlusion copy) kernel.
  * Warp roles: warps [0, DBOT_CW) compute; in update launches warps [DBOT_CW, DBOT_CW+DBOT_SW)
- * stream the parent's propagated occlusion image into the child's slot while the compute warps
- * transform and rasterise the same particle; the compute warps then overwrite the covered
- * pixels with the posterior.  Hand-off through two named barriers (copied / consumed). */
+ * copy the parent's stored occlusion image into the child's slot -- for the children that do not
+ * adopt their parent's slot (dbot_plan_update_kernel) -- while the compute warps transform and
+ * rasterise the same particle; the compute warps then overwrite the covered pixels with the
+ * (lazily encoded) posterior.  Hand-off through two named barriers (copied / consumed); an
+ * adopting child additionally waits on its parent's pending counter. */
 template <int MODE, bool MULTI> /* MULTI: the mesh is split into several chunks (big or multi-object) */
 __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST : 0), 1)
     dbot_particle_kernel(const __grid_constant__ dbot_kparams p)
