@@ -116,6 +116,12 @@ def test_argument_errors_need_no_device():
     cfg, keep = abi.make_config(60, 80, synth.camera_matrix(8), 4, V, T, **dict(kw), occlusion_mode=1)
     assert lib.dbot_b200_create(C.byref(cfg), C.byref(h)) == -2       # reserved mode
     assert h.value is None
+    f = C.c_void_p()
+    fc = abi.FilterConfig()
+    assert lib.dbot_b200_filter_create(None, C.byref(fc), C.byref(f)) == -1 and f.value is None
+    assert lib.dbot_b200_filter_track(None, None, None, None) == -1
+    assert lib.dbot_b200_export_slot_device(None, 0, None) == -1
+    assert lib.dbot_b200_slot_floats(None) == -1
     assert lib.dbot_b200_reset(None) == -1
     assert lib.dbot_b200_loglikes(None, None, None, 0, 0, None) == -1
     assert lib.dbot_b200_n_slots(None) == -1

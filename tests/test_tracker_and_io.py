@@ -160,3 +160,25 @@ def test_device_resident_filter_matches_the_host_loop_and_tracks():
     assert err[-6:].max() < 0.004, err
     assert dev.resample_count >= 1 and abs(dev.resample_count - host.resample_count) <= 2
     assert s_dev.n_slots == 300
+
+
+@pytest.mark.gpu
+def test_device_filter_argument_errors():
+    from dbot_ros_b200 import DbotB200Error
+    from dbot_ros_b200.tracker import DeviceParticleTracker
+
+    rows, cols = synth.resolution(8)
+    V, T = synth.mesh_set("ico80")
+    sensor = RbSensorBuilder(ObjectModel(V, T), CameraData(synth.camera_matrix(8), rows, cols),
+                             Parameters(sample_count=16)).build()
+    with pytest.raises(DbotB200Error):                      # more particles than the sensor was built for
+        DeviceParticleTracker(sensor, TrackerParameters(evaluation_count=17))
+    trk = DeviceParticleTracker(sensor, TrackerParameters(evaluation_count=16), seed=3)
+    trk.initialize([[0.0, 0.0, 0.8, 0.0, 0.0, 0.0]])
+    frame = synth.make_frame(sensor.render, [(np.eye(3), np.array([0.0, 0.0, 0.8]))], rows, cols,
+                             np.random.default_rng(0), occluder=False)
+    a = trk.track(frame)
+    trk.initialize([[0.0, 0.0, 0.8, 0.0, 0.0, 0.0]])        # same seed, same frame counter: same result
+    b = trk.track(frame)
+    assert np.array_equal(a, b) and np.linalg.norm(a[0, :3] - [0, 0, 0.8]) < 0.01
+    trk.close()
