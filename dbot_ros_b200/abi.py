@@ -43,6 +43,7 @@ class Config(C.Structure):
         ("delta_time", C.c_double),
         ("device_id", C.c_int32),
         ("occlusion_mode", C.c_int32),
+        ("cull_backfaces", C.c_int32),
     ]
 
 
@@ -80,6 +81,7 @@ SIGNATURES = {
     "dbot_b200_filter_initialize": (C.c_int, [_P, _P]),
     "dbot_b200_filter_track": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int32)]),
     "dbot_b200_n_slots": (C.c_int, [_P]),
+    "dbot_b200_cull_sign": (C.c_int, [_P, C.c_int32]),
     "dbot_b200_observation_time": (C.c_double, [_P]),
     "dbot_b200_free_slot_count": (C.c_int, [_P]),
     "dbot_b200_get_occlusion": (C.c_int, [_P, C.c_int32, _P]),
@@ -125,7 +127,7 @@ def check(lib, rc):
 def make_config(rows, cols, K, max_particles, vertices, triangles, *, tail_weight, model_sigma,
                 sigma_factor, half_life_depth, max_depth, p_occluded_visible, p_occluded_occluded,
                 initial_occlusion_prob, delta_time, device_id=0, occlusion_mode=0,
-                struct=Config):
+                cull_backfaces=0, struct=Config):
     """Fill a dbot_b200_config (or a layout-compatible struct).  Returns (cfg, keepalive)."""
     n_obj = len(vertices)
     v_arr = [np.ascontiguousarray(v, dtype=np.float32).reshape(-1, 3) for v in vertices]
@@ -161,6 +163,8 @@ def make_config(rows, cols, K, max_particles, vertices, triangles, *, tail_weigh
         cfg.device_id = int(device_id)
     if hasattr(cfg, "occlusion_mode"):
         cfg.occlusion_mode = int(occlusion_mode)
+    if hasattr(cfg, "cull_backfaces") and struct is Config:
+        cfg.cull_backfaces = int(cull_backfaces)
     return cfg, (v_arr, t_arr, vp, tp, nv, nt)
 
 

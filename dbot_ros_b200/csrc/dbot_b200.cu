@@ -69,7 +69,8 @@ enum
 
 struct dbot_chunk
 {
-    int32_t obj, n_verts, n_tris, pad;
+    int32_t obj, n_verts, n_tris;
+    int32_t cull_sign; /* back-face culling: sign of the snapped area of the triangles to keep, 0 = all */
     uint32_t vert_off, vert_bytes; /* byte offsets into the packed device mesh, 16 B aligned */
     uint32_t tri_off, tri_bytes;
 };
@@ -97,7 +98,7 @@ struct dbot_kparams
     float* depth_out;       /* render: [rows*cols] */
     int* err_flag;
     /* shared-memory carve-up (bytes from the dynamic smem base) */
-    uint32_t off_tri, off_v4, off_Y, off_wt;
+    uint32_t off_tri, off_v4, off_XY, off_list, off_rec, off_wt;
     uint32_t wcap;          /* inverse-depth tile capacity in pixels */
 };
 
@@ -136,6 +137,7 @@ struct dbot_b200_sensor
     cudaStream_t stream;
     dbot_kparams kp; /* template: per-call fields are filled at launch */
     int grid_max, smem_bytes, num_sms;
+    int cull_signs[DBOT_B200_MAX_OBJECTS];
     /* model constants */
     double lambda, wD, c, log_c;
     /* device memory */
@@ -183,23 +185,106 @@ struct dbot_b200_sensor
 
 static uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
+/* Back-face culling is applied to an object only when its mesh is PROVEN closed and consistently
+ * oriented: after welding vertices with bit-identical positions, every directed edge u->v must occur
+ * exactly once and its opposite v->u exactly once; every connected component must enclose volume
+ * of the same sign.  Then along any ray from outside the nearest surface is camera-facing, so
+ * dropping the triangles that face away leaves the depth image unchanged (up to the rounding that
+ * decides between the two triangles meeting at a silhouette edge; quantified in tests/).  dbot's
+ * renderer draws every triangle; open, inside-out-in-parts or non-manifold meshes are therefore
+ * rendered exactly as before (return 0).  Returns the sign of the snapped screen-space area
+ * (x right, y down) of the triangles to keep. */
+static int mesh_cull_sign(const float* V, int nv, const int32_t* T, int nt, double fxfy)
+{
+    if (nv < 4 || nt < 4) return 0;
+    struct key3
+    {
+        uint32_t a, b, c;
+        bool operator==(const key3& o) const { return a == o.a && b == o.b && c == o.c; }
+    };
+    struct hash3
+    {
+        size_t operator()(const key3& k) const
+        {
+            uint64_t h = k.a * 0x9E3779B97F4A7C15ull;
+            h ^= (h >> 29) + k.b * 0xBF58476D1CE4E5B9ull;
+            h ^= (h >> 31) + k.c * 0x94D049BB133111EBull;
+            return (size_t)(h ^ (h >> 32));
+        }
+    };
+    std::unordered_map<key3, int32_t, hash3> weld;
+    std::vector<int32_t> canon((size_t)nv);
+    for (int i = 0; i < nv; ++i)
+    {
+        key3 k;
+        memcpy(&k, V + 3 * (size_t)i, sizeof(k));
+        canon[i] = weld.emplace(k, i).first->second;
+    }
+    std::unordered_map<uint64_t, int32_t> edge_tri; /* directed edge -> triangle */
+    edge_tri.reserve((size_t)nt * 3);
+    auto ekey = [](int32_t u, int32_t v) { return ((uint64_t)(uint32_t)u << 32) | (uint32_t)v; };
+    for (int t = 0; t < nt; ++t)
+    {
+        const int32_t a = canon[T[3 * t]], b = canon[T[3 * t + 1]], c = canon[T[3 * t + 2]];
+        if (a == b || b == c || c == a) return 0;
+        const int32_t e[3][2] = {{a, b}, {b, c}, {c, a}};
+        for (auto& uv : e)
+            if (!edge_tri.emplace(ekey(uv[0], uv[1]), t).second) return 0; /* used twice in one direction */
+    }
+    std::vector<int32_t> parent((size_t)nt);
+    for (int t = 0; t < nt; ++t) parent[t] = t;
+    auto find = [&](int32_t i) {
+        while (parent[i] != i) i = parent[i] = parent[parent[i]];
+        return i;
+    };
+    for (const auto& kv : edge_tri)
+    {
+        const int32_t u = (int32_t)(kv.first >> 32), v = (int32_t)(kv.first & 0xffffffffu);
+        auto opp = edge_tri.find(ekey(v, u));
+        if (opp == edge_tri.end()) return 0; /* boundary edge */
+        const int32_t ra = find(kv.second), rb = find(opp->second);
+        if (ra != rb) parent[ra] = rb;
+    }
+    std::vector<double> vol((size_t)nt, 0.0);
+    for (int t = 0; t < nt; ++t)
+    {
+        const float *a = V + 3 * (size_t)T[3 * t], *b = V + 3 * (size_t)T[3 * t + 1], *c = V + 3 * (size_t)T[3 * t + 2];
+        vol[find(t)] += (double)a[0] * ((double)b[1] * c[2] - (double)b[2] * c[1]) +
+                        (double)a[1] * ((double)b[2] * c[0] - (double)b[0] * c[2]) +
+                        (double)a[2] * ((double)b[0] * c[1] - (double)b[1] * c[0]);
+    }
+    int sgn = 0;
+    for (int t = 0; t < nt; ++t)
+    {
+        if (find(t) != t) continue;
+        const int sv = vol[t] > 0.0 ? 1 : (vol[t] < 0.0 ? -1 : 0);
+        if (sv == 0 || (sgn != 0 && sv != sgn)) return 0;
+        sgn = sv;
+    }
+    /* outward-oriented triangles facing the camera have negative area where x grows to the right and y
+     * downwards (fx fy > 0); a mirrored image flips that */
+    return fxfy > 0.0 ? -sgn : sgn;
+}
+
 /* split every object mesh into chunks of at most DBOT_CHUNK_MAX_VERTS vertices and
  * DBOT_CHUNK_MAX_TRIS triangles with chunk-local uint16 indices (shared vertices are
  * duplicated; a duplicated vertex transforms to bit-identical coordinates).  Vertices are
  * stored as float4 (read once per particle straight from L2), triangle lists as uint16
  * triples (TMA-staged into shared memory). */
 static int build_chunks(const dbot_b200_config* cfg, std::vector<dbot_chunk>& chunks,
-                        std::vector<unsigned char>& blob)
+                        std::vector<unsigned char>& blob, int* cull_signs)
 {
     for (int o = 0; o < cfg->n_objects; ++o)
     {
         const int nv = cfg->n_vertices[o], nt = cfg->n_triangles[o];
+        cull_signs[o] = 0;
         if (nv < 0 || nt < 0) return fail(-2, "object %d: negative vertex/triangle count", o);
         const float* V = cfg->vertices[o];
         const int32_t* T = cfg->triangles[o];
         if ((nv > 0 && !V) || (nt > 0 && !T)) return fail(-1, "object %d: null mesh pointer", o);
         for (int i = 0; i < 3 * nt; ++i)
             if (T[i] < 0 || T[i] >= nv) return fail(-6, "object %d: triangle index out of range", o);
+        if (cfg->cull_backfaces == 0) cull_signs[o] = mesh_cull_sign(V, nv, T, nt, cfg->K[0] * cfg->K[4]);
         int t = 0;
         while (t < nt)
         {
@@ -232,6 +317,7 @@ static int build_chunks(const dbot_b200_config* cfg, std::vector<dbot_chunk>& ch
             dbot_chunk ch;
             memset(&ch, 0, sizeof(ch));
             ch.obj = o;
+            ch.cull_sign = cull_signs[o];
             ch.n_verts = (int)cv.size() / 4;
             ch.n_tris = (int)ct.size() / 3;
             ch.vert_bytes = round_up((uint32_t)(cv.size() * sizeof(float)), 16);
@@ -311,7 +397,7 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     /* mesh */
     std::vector<dbot_chunk> chunks;
     std::vector<unsigned char> blob;
-    int rc = build_chunks(cfg, chunks, blob);
+    int rc = build_chunks(cfg, chunks, blob, s->cull_signs);
     if (rc) return rc;
     CUDA_TRY(cudaMalloc(&s->d_mesh, blob.size()));
     CUDA_TRY(cudaMemcpy(s->d_mesh, blob.data(), blob.size(), cudaMemcpyHostToDevice));
@@ -356,10 +442,12 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     uint32_t off = 0;
     kp.off_tri = off; off += round_up((uint32_t)max_nt * 6u, 128);
     kp.off_v4 = off;  off += round_up((uint32_t)max_nv * 16u, 128);
-    kp.off_Y = off;   off += round_up((uint32_t)max_nv * 4u, 128);
+    kp.off_XY = off;  off += round_up((uint32_t)max_nv * 8u, 128);
+    kp.off_list = off; off += round_up((uint32_t)max_nt * 2u, 128);
+    kp.off_rec = off; off += DBOT_CW * 32u * DBOT_REC_WORDS * 4u;
     kp.off_wt = off;
-    /* static __shared__ (owner tables, dummy words, hand-off) + slack */
-    const int smem_max = (int)prop.sharedMemPerBlockOptin - 1024 - DBOT_CW * DBOT_OWNER_CAP - DBOT_CW * 128;
+    /* static __shared__ (first-row masks, counters, hand-off) + slack */
+    const int smem_max = (int)prop.sharedMemPerBlockOptin - 1024 - DBOT_CW * 128 - DBOT_CW * 8 - 256;
     if ((int)off + 4 * (int)round_up((uint32_t)kp.cols, 4) > smem_max)
         return fail(-9, "image too wide for the shared-memory depth tile (cols=%d)", kp.cols);
     s->smem_bytes = smem_max;
@@ -430,6 +518,10 @@ extern "C" int dbot_b200_create(const dbot_b200_config* cfg, dbot_b200_sensor** 
     if (!(cfg->half_life_depth > 0.0) || !(cfg->max_depth > 0.0) || !(cfg->model_sigma > 0.0))
         return fail(-4, "create: half_life_depth, max_depth and model_sigma must be positive");
     if (cfg->occlusion_mode != 0) return fail(-2, "create: occlusion_mode %d is reserved", cfg->occlusion_mode);
+    if (cfg->cull_backfaces != 0 && cfg->cull_backfaces != 1)
+        return fail(-2, "create: cull_backfaces must be 0 (where proven safe) or 1 (never)");
+    /* the span records pack pixel coordinates into 16 bits */
+    if (cfg->rows > 32768 || cfg->cols > 32768) return fail(-2, "create: resolution %dx%d above 32768", cfg->cols, cfg->rows);
     dbot_b200_sensor* s = new dbot_b200_sensor();
     memset(s, 0, sizeof(*s));
     s->cfg = *cfg;
@@ -756,6 +848,10 @@ extern "C" int dbot_b200_render(dbot_b200_sensor* s, const float* pose, float* o
 
 /* ---- state read-back ---- */
 extern "C" int dbot_b200_n_slots(dbot_b200_sensor* s) { return s ? s->n_slots : -1; }
+extern "C" int dbot_b200_cull_sign(dbot_b200_sensor* s, int32_t object)
+{
+    return (s && object >= 0 && object < s->cfg.n_objects) ? s->cull_signs[object] : 0;
+}
 extern "C" double dbot_b200_observation_time(dbot_b200_sensor* s) { return s ? s->t_obs : NAN; }
 
 /* ---- occlusion-slot migration between handles (cross-GPU resampling) ---- */

@@ -6,197 +6,248 @@
 
 /* ------------------------------------------------------------------------------------------ */
 /* raster: the triangles of one staged chunk into the inverse-depth tile covering rows
- * [row0,row1] x columns [col0,col1].
+ * [row0,row1] x columns [col0,col1].  Three steps, all in shared memory:
  *
- * A warp takes 32 triangles at a time (batches handed out by a shared-memory counter); every
- * lane sets its own triangle up (convergent).  The pixel boxes of the 32 triangles are cut into
- * blocks of 8 columns x 4 rows and the blocks are dealt out evenly over the lanes (prefix sum
- * over the block counts, owner table in shared memory, owner's parameters by shuffle), so every
- * lane always has a block to work on however unequal the triangles are.  A block is processed
- * row by row without any branch: 8 x (three int32 edge functions, sign test, one fma for the
- * inverse depth, address select, shared-memory max on the bits of the positive float).
- * Pixels of a block outside the triangle's own box fail the edge test by themselves, so no
- * box mask is needed -- unless the box was cut by the raster window; those triangles, the ones
- * that need int64 edge functions and the ones with more than DBOT_BIG_BLOCKS blocks are instead
- * walked by the whole warp, 8 x 4 pixels per step with explicit bounds.                        */
+ * 1. prepass (whole CTA, one triangle per thread and step): snapped vertices -> validity,
+ *    orientation (back faces of a mesh proven closed are dropped here and never set up), pixel box
+ *    clipped to the tile.  Survivors are appended to a compact list with one shared-memory atomic
+ *    per warp (ballot + popc); the few triangles that do not fit a batch lane (more than
+ *    DBOT_SPAN_BATCH_ROWS rows, or int64 edge functions) go to the back of the same list.
+ * 2. set-up (a warp takes 32 survivors at a time, one per lane): plane equation bit for bit as the
+ *    oracle, the three edges sorted into long / short as dbot_setup_spans describes, one 80-byte
+ *    span record per triangle in the warp's record buffer.
+ * 3. units: the pixel rows of the 32 triangles are dealt out evenly over the lanes -- unit q of the
+ *    batch is row q - first_row(owner) of its owner, the owner being found from a 1024-bit mask of
+ *    first rows (one word per lane) by two shuffles and a popc.  A unit reads its owner's record
+ *    (four conflict-free LDS), computes the exact first and last covered column of its row
+ *    (dbot_row_span) and sends only those pixels' inverse depths to the tile's max
+ *    (red.shared.max on the bits of the positive float).  No pixel outside a triangle is ever
+ *    tested: 35 k fragments and 15 k row units per particle for the 5120-triangle mesh, where the
+ *    block sweep of round 1 tested 385 k pixels.                                              */
 #define DBOT_BOX_CHUNKS 32 /* chunks beyond this many are never culled against a tile */
-#define DBOT_OWNER_CAP 512 /* blocks per batch: 32 lanes x at most 16 blocks each */
-#define DBOT_BIG_BLOCKS 16 /* a triangle with more blocks than a lane's share of the table: whole-warp walk */
+#define DBOT_REC_WORDS 20  /* span record: five 16-byte quarters; a stride of 20 words keeps the
+                              quarter loads of up to 8 different records in a phase conflict-free */
+#define DBOT_LIST_WIDE 0x8000u /* flag in the survivor list: int64 block walk instead of span units */
 
 __device__ __forceinline__ void dbot_zmax(uint32_t* p, uint32_t v)
 {
     if (v > *p) atomicMax(p, v); /* plain read first: fragments that lose the test cost no atomic */
 }
-__device__ __forceinline__ void dbot_raster_chunk(const uint16_t* __restrict__ s_tri, int ntri,
-                                                  const float4* __restrict__ s_v4,
-                                                  const int* __restrict__ s_Y, const dbot_camera& K,
-                                                  uint32_t* s_wt, unsigned char* s_owner, int* s_batch,
+
+struct dbot_raster_smem
+{
+    const uint16_t* tri;  /* [ntri][3] chunk-local vertex indices (TMA-staged) */
+    const float4* v4;     /* [nv] camera-frame x, y, z and 1/z */
+    const int2* XY;       /* [nv] snapped image position */
+    uint16_t* list;       /* [ntri] survivors from the front, tall / wide triangles from the back */
+    uint32_t* rec;        /* this warp's record buffer, 32 x DBOT_REC_WORDS words */
+    uint32_t* mask;       /* this warp's first-row mask, 32 words */
+    uint32_t* wt;         /* inverse-depth tile */
+    int* counters;        /* [0] survivors, [1] tall + wide, [2] next batch */
+};
+
+__device__ __forceinline__ dbot_vertex dbot_load_vertex(const dbot_raster_smem& S, int i)
+{
+    const float4 a = S.v4[i];
+    const int2 b = S.XY[i];
+    dbot_vertex v;
+    v.x = a.x; v.y = a.y; v.z = a.z; v.iz = a.w; v.X = b.x; v.Y = b.y;
+    return v;
+}
+
+/* step 1; every compute thread calls it, then a compute_sync() publishes the list */
+__device__ __forceinline__ void dbot_raster_prepass(const dbot_raster_smem& S, int ntri, int cull_sign,
+                                                    int row0, int row1, int col0, int col1, int tid)
+{
+    const int lane = tid & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = tid - lane; base < ntri; base += DBOT_CT)
+    {
+        const int t = base + lane;
+        int kind = DBOT_TRI_REJECT;
+        if (t < ntri)
+        {
+            const int2 a = S.XY[S.tri[3 * t]], b = S.XY[S.tri[3 * t + 1]], c = S.XY[S.tri[3 * t + 2]];
+            int cmin, cmax, rmin, rmax;
+            kind = dbot_prepass_triangle(a.x, a.y, b.x, b.y, c.x, c.y, cull_sign, row0, row1, col0, col1,
+                                         cmin, cmax, rmin, rmax);
+        }
+        const unsigned m_front = __ballot_sync(DBOT_FULL, kind == DBOT_TRI_SPANS);
+        const unsigned m_back = __ballot_sync(DBOT_FULL, kind >= DBOT_TRI_TALL);
+        int b_front = 0, b_back = 0;
+        if (lane == 0)
+        {
+            if (m_front) b_front = atomicAdd(&S.counters[0], __popc(m_front));
+            if (m_back) b_back = atomicAdd(&S.counters[1], __popc(m_back));
+        }
+        b_front = __shfl_sync(DBOT_FULL, b_front, 0);
+        b_back = __shfl_sync(DBOT_FULL, b_back, 0);
+        if (kind == DBOT_TRI_SPANS)
+            S.list[b_front + __popc(m_front & lt)] = (uint16_t)t;
+        else if (kind >= DBOT_TRI_TALL)
+            S.list[ntri - 1 - (b_back + __popc(m_back & lt))] =
+                (uint16_t)(t | (kind == DBOT_TRI_WIDE ? DBOT_LIST_WIDE : 0u));
+    }
+}
+
+/* one (triangle, row) unit: record at `rec` (shared-memory byte address), row j of its box;
+ * pa = first unit of the owner | aux << 11 (dbot_span_rec::aux) */
+__device__ __forceinline__ void dbot_span_unit(uint32_t rec, int j, int aux, bool active, uint32_t tile_s,
+                                               int row0, int col0, int ww)
+{
+    const int bwm1 = aux & 0xff, split = (aux >> 8) & 0xff;
+    const bool long_left = (aux >> 16) & 1;
+    const uint32_t short_q = rec + (j >= split ? 32u : 16u);
+    const uint32_t left_q = long_left ? rec : short_q, right_q = long_left ? short_q : rec;
+    dbot_edge L, R;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(L.g0), "=r"(L.gr), "=r"(L.gc), "=f"(L.nrc) : "r"(left_q));
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(R.g0), "=r"(R.gr), "=r"(R.gc), "=f"(R.nrc) : "r"(right_q));
+    float m0, m1, m2, wlo, whi;
+    int org;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4+48];" : "=f"(m0), "=f"(m1), "=f"(m2), "=r"(org) : "r"(rec));
+    asm volatile("ld.shared.v2.b32 {%0,%1}, [%2+64];" : "=f"(wlo), "=f"(whi) : "r"(rec));
+    int first;
+    int n = dbot_row_span(L, R, j, bwm1, first);
+    if (!active) n = 0;
+    if (n > 0)
+    {
+        const int r = (org >> 16) + j, c = (org & 0xffff) + first;
+        const float wr = dbot_fmaf(m1, (float)r, m2);
+        float fc = (float)c;
+        uint32_t addr = tile_s + 4u * (uint32_t)((r - row0) * ww + (c - col0));
+        do
+        {
+            const uint32_t bits = dbot_f2u(fminf(fmaxf(dbot_fmaf(m0, fc, wr), wlo), whi));
+            asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(addr), "r"(bits) : "memory");
+            fc = dbot_add(fc, 1.0f);
+            addr += 4u;
+        } while (--n);
+    }
+}
+
+__device__ __forceinline__ void dbot_store_record(uint32_t* dst, const dbot_span_rec& s)
+{
+    uint4* q = reinterpret_cast<uint4*>(dst);
+    q[0] = make_uint4((uint32_t)s.A.g0, (uint32_t)s.A.gr, (uint32_t)s.A.gc, __float_as_uint(s.A.nrc));
+    q[1] = make_uint4((uint32_t)s.B1.g0, (uint32_t)s.B1.gr, (uint32_t)s.B1.gc, __float_as_uint(s.B1.nrc));
+    q[2] = make_uint4((uint32_t)s.B2.g0, (uint32_t)s.B2.gr, (uint32_t)s.B2.gc, __float_as_uint(s.B2.nrc));
+    q[3] = make_uint4(__float_as_uint(s.m0), __float_as_uint(s.m1), __float_as_uint(s.m2), (uint32_t)s.org);
+    q[4] = make_uint4(__float_as_uint(s.wlo), __float_as_uint(s.whi), (uint32_t)s.aux, 0u);
+}
+
+/* steps 2 and 3; called by every compute warp after the prepass has been published */
+__device__ __forceinline__ void dbot_raster_sweep(const dbot_raster_smem& S, int ntri, const dbot_camera& K,
                                                   int row0, int row1, int col0, int col1, int lane)
 {
     const int ww = col1 - col0 + 1;
-    const uint32_t tile_s = smem_u32(s_wt);
-    /* dummy words: 8 consecutive ones per lane (the column offset stays an immediate of the atomic),
-     * staggered so that the 32 lanes of a warp hit 32 different banks at every column; one set serves
-     * all warps -- a warp instruction owns the shared-memory pipe while it executes */
-    __shared__ uint32_t s_dummy[8 * 31 + 7 + 8];
-    const uint32_t dummy_s = smem_u32(&s_dummy[8 * lane + (lane >> 2)]);
+    const uint32_t tile_s = smem_u32(S.wt);
+    const uint32_t rec_s = smem_u32(S.rec);
+    const int n_front = S.counters[0], n_back = S.counters[1];
+    const int front_batches = (n_front + 31) >> 5;
+    const unsigned le = 0xffffffffu >> (31 - lane);
     for (;;)
     {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(s_batch, 32);
-        base = __shfl_sync(DBOT_FULL, base, 0);
-        if (base >= ntri) break;
-        const int t = base + lane;
-        dbot_tri s;
-        bool ok = false;
-        if (t < ntri)
-        {
-            const int ia = s_tri[3 * t], ib = s_tri[3 * t + 1], ic = s_tri[3 * t + 2];
-            const float4 pa = s_v4[ia], pb = s_v4[ib], pc = s_v4[ic];
-            dbot_vertex a, b, c;
-            a.x = pa.x; a.y = pa.y; a.z = pa.z; a.X = __float_as_int(pa.w); a.Y = s_Y[ia];
-            b.x = pb.x; b.y = pb.y; b.z = pb.z; b.X = __float_as_int(pb.w); b.Y = s_Y[ib];
-            c.x = pc.x; c.y = pc.y; c.z = pc.z; c.X = __float_as_int(pc.w); c.Y = s_Y[ic];
-            ok = dbot_setup_triangle(a, b, c, K, row0, row1, col0, col1, s);
-        }
-        __syncwarp();
-        const int bw = ok ? (s.cmax - s.cmin + 8) >> 3 : 0; /* blocks of 8 columns */
-        const int bh = ok ? (s.rmax - s.rmin + 4) >> 2 : 0; /* blocks of 4 rows */
-        /* whole-warp walk: int64 edge functions, window-cut boxes, more blocks than a lane's share of the owner table */
-        const bool big = ok && (!s.small || s.clipped || bw * bh > DBOT_BIG_BLOCKS);
-        const bool mine = ok && !big;
-        const int nb = mine ? bw * bh : 0;
+        int batch = 0;
+        if (lane == 0) batch = atomicAdd(&S.counters[2], 1);
+        batch = __shfl_sync(DBOT_FULL, batch, 0);
+        if (batch >= front_batches + n_back) break;
 
-        /* edge functions at (cmin, rmin), oriented so that inside means all three >= 0 */
-        int e0c = 0, e1c = 0, e2c = 0, e0r = 0, e1r = 0, e2r = 0, A0 = -1, A1 = -1, A2 = -1;
-        if (mine)
+        /* ---- which triangles: 32 survivors, or one tall / wide triangle from the back ---- */
+        int t = -1;
+        bool wide = false;
+        if (batch < front_batches)
         {
-            e0c = -(s.Yb - s.Ya) * DBOT_SUBPIX; e0r = (s.Xb - s.Xa) * DBOT_SUBPIX;
-            e1c = -(s.Yc - s.Yb) * DBOT_SUBPIX; e1r = (s.Xc - s.Xb) * DBOT_SUBPIX;
-            e2c = -(s.Ya - s.Yc) * DBOT_SUBPIX; e2r = (s.Xa - s.Xc) * DBOT_SUBPIX;
-            const int px0 = s.cmin * DBOT_SUBPIX, py0 = s.rmin * DBOT_SUBPIX;
-            A0 = (s.Xb - s.Xa) * (py0 - s.Ya) - (s.Yb - s.Ya) * (px0 - s.Xa);
-            A1 = (s.Xc - s.Xb) * (py0 - s.Yb) - (s.Yc - s.Yb) * (px0 - s.Xb);
-            A2 = (s.Xa - s.Xc) * (py0 - s.Yc) - (s.Ya - s.Yc) * (px0 - s.Xc);
-            if (s.flip)
-            {
-                A0 = -A0; A1 = -A1; A2 = -A2;
-                e0c = -e0c; e1c = -e1c; e2c = -e2c;
-                e0r = -e0r; e1r = -e1r; e2r = -e2r;
-            }
+            const int k = 32 * batch + lane;
+            if (k < n_front) t = S.list[k];
         }
-        /* origin of the box and its width in blocks, packed: cmin | rmin << 12 | bw << 24 */
-        const int origin = mine ? (s.cmin | (s.rmin << 12) | (bw << 24)) : 0;
-        /* inclusive prefix sum of the block counts, owner table */
-        int P = nb;
+        else
+        {
+            const unsigned e = S.list[ntri - 1 - (batch - front_batches)];
+            wide = (e & DBOT_LIST_WIDE) != 0;
+            if (lane == 0 || wide) t = (int)(e & (DBOT_LIST_WIDE - 1u));
+        }
+        if (wide)
+        {
+            /* int64 edge functions: the whole warp walks the box, 8 x 4 pixels per step */
+            const dbot_vertex a = dbot_load_vertex(S, S.tri[3 * t]), b = dbot_load_vertex(S, S.tri[3 * t + 1]),
+                              c = dbot_load_vertex(S, S.tri[3 * t + 2]);
+            dbot_tri q;
+            if (dbot_setup_triangle(a, b, c, K, row0, row1, col0, col1, q))
+            {
+                const int dc = lane & 7, dr = lane >> 3;
+                for (int r0 = q.rmin; r0 <= q.rmax; r0 += 4)
+                {
+                    const int r = r0 + dr;
+                    for (int c0 = q.cmin; c0 <= q.cmax; c0 += 8)
+                    {
+                        const int cc = c0 + dc;
+                        if (r <= q.rmax && cc <= q.cmax && dbot_covers(q, cc, r))
+                            dbot_zmax(S.wt + (r - row0) * ww + (cc - col0), dbot_fragment_w(q, (float)cc, (float)r));
+                    }
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+
+        /* ---- set-up: one triangle per lane -> span record in the warp's buffer ---- */
+        int nrows = 0, aux = 0;
+        if (t >= 0)
+        {
+            const dbot_vertex a = dbot_load_vertex(S, S.tri[3 * t]), b = dbot_load_vertex(S, S.tri[3 * t + 1]),
+                              c = dbot_load_vertex(S, S.tri[3 * t + 2]);
+            int cmin = dbot_ceil_subpix(dbot_min3(a.X, b.X, c.X)), cmax = dbot_floor_subpix(dbot_max3(a.X, b.X, c.X));
+            int rmin = dbot_ceil_subpix(dbot_min3(a.Y, b.Y, c.Y)), rmax = dbot_floor_subpix(dbot_max3(a.Y, b.Y, c.Y));
+            cmin = max(cmin, col0); cmax = min(cmax, col1);
+            rmin = max(rmin, row0); rmax = min(rmax, row1);
+            dbot_span_rec s;
+            dbot_setup_spans(a, b, c, K, cmin, cmax, rmin, rmax, s);
+            dbot_store_record(S.rec + DBOT_REC_WORDS * lane, s);
+            nrows = rmax - rmin + 1;
+            aux = s.aux;
+        }
+        /* first unit of every lane's triangle (exclusive prefix sum of the row counts) */
+        int P = nrows;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1)
         {
             const int v = __shfl_up_sync(DBOT_FULL, P, d);
             if (lane >= d) P += v;
         }
-#ifdef DBOT_DBG_NO_SWEEP
-        const int H = (A0 == 0x7654321) ? 1 : 0;
-#else
         const int H = __shfl_sync(DBOT_FULL, P, 31);
-#endif
-        const int Pex = P - nb;
-        for (int k = 0; k < nb; ++k) s_owner[Pex + k] = (unsigned char)lane;
+        const int Pex = P - nrows;
+        /* bit q of the mask: a triangle starts at unit q */
+        S.mask[lane] = 0u;
         __syncwarp();
+        if (nrows > 0) atomicOr(&S.mask[Pex >> 5], 1u << (Pex & 31));
+        __syncwarp();
+        const uint32_t word = S.mask[lane];
+        int wpre = __popc(word);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const int v = __shfl_up_sync(DBOT_FULL, wpre, d);
+            if (lane >= d) wpre += v;
+        }
+        wpre -= __popc(word);
+        const int pa = Pex | (aux << 11);
 
+        /* ---- units ---- */
         for (int qb = 0; qb < H; qb += 32)
         {
             const int q = qb + lane;
-            const bool active = q < H;
-            const int j = active ? s_owner[q] : 0;
-            const int idx = q - __shfl_sync(DBOT_FULL, Pex, j);
-            const int o_origin = __shfl_sync(DBOT_FULL, origin, j);
-            int o_e0c = __shfl_sync(DBOT_FULL, e0c, j), o_e1c = __shfl_sync(DBOT_FULL, e1c, j),
-                o_e2c = __shfl_sync(DBOT_FULL, e2c, j);
-            int o_e0r = __shfl_sync(DBOT_FULL, e0r, j);
-            const int o_e1r = __shfl_sync(DBOT_FULL, e1r, j), o_e2r = __shfl_sync(DBOT_FULL, e2r, j);
-            const int o_A0 = __shfl_sync(DBOT_FULL, A0, j), o_A1 = __shfl_sync(DBOT_FULL, A1, j),
-                      o_A2 = __shfl_sync(DBOT_FULL, A2, j);
-            const float o_m0 = __shfl_sync(DBOT_FULL, s.m0, j), o_m1 = __shfl_sync(DBOT_FULL, s.m1, j),
-                        o_m2 = __shfl_sync(DBOT_FULL, s.m2, j);
-            const float o_wlo = __shfl_sync(DBOT_FULL, s.wlo, j), o_whi = __shfl_sync(DBOT_FULL, s.whi, j);
-            const int o_bw = o_origin >> 24;
-            /* idx -> (row block, column block); exact for these small integers */
-            const int pr = (o_bw == 1) ? idx : __float2int_rz(__fdividef((float)idx + 0.5f, (float)o_bw));
-            const int bx = idx - pr * o_bw;
-            const int cx0 = (o_origin & 0xfff) + 8 * bx, ry0 = ((o_origin >> 12) & 0xfff) + 4 * pr;
-            int x0 = o_A0 + (8 * bx) * o_e0c + (4 * pr) * o_e0r;
-            int x1 = o_A1 + (8 * bx) * o_e1c + (4 * pr) * o_e1r;
-            int x2 = o_A2 + (8 * bx) * o_e2c + (4 * pr) * o_e2r;
-            if (!active) /* nothing to do in the last, partial round: every test fails */
-            {
-                x0 = -1;
-                o_e0c = 0;
-                o_e0r = 0;
-            }
-            const float fc0 = (float)cx0;
-            float fr = (float)ry0;
-            uint32_t trow = tile_s + 4u * (uint32_t)((ry0 - row0) * ww + (cx0 - col0));
-            float fc[8];
-#pragma unroll
-            for (int cc = 0; cc < 8; ++cc) fc[cc] = dbot_add(fc0, (float)cc);
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr)
-            {
-                const float wr = dbot_fmaf(o_m1, fr, o_m2);
-                /* Branch-free resolve.  ptxas wraps every predicated shared-memory atomic in a
-                 * BSSY/BRA/BSYNC triple, and a read-compare-branch in front of it costs more issue
-                 * slots than the atomics it saves; so every covered pixel sends its inverse depth
-                 * to the tile's max, and every pixel outside the triangle sends it to a per-lane
-                 * dummy word instead (own bank: no conflict, no branch). */
-#define DBOT_SWEEP_PIXEL(cc)                                                                          \
-    {                                                                                                  \
-        const int eor = (x0 + (cc) * o_e0c) | (x1 + (cc) * o_e1c) | (x2 + (cc) * o_e2c);              \
-        const uint32_t bits = dbot_f2u(fminf(fmaxf(dbot_fmaf(o_m0, fc[cc], wr), o_wlo), o_whi));       \
-        const uint32_t a = eor >= 0 ? trow : dummy_s;                                                   \
-        asm volatile("red.shared.max.u32 [%0+%2], %1;" ::"r"(a), "r"(bits), "n"(4 * (cc)) : "memory"); \
-    }
-                DBOT_SWEEP_PIXEL(0) DBOT_SWEEP_PIXEL(1) DBOT_SWEEP_PIXEL(2) DBOT_SWEEP_PIXEL(3)
-                DBOT_SWEEP_PIXEL(4) DBOT_SWEEP_PIXEL(5) DBOT_SWEEP_PIXEL(6) DBOT_SWEEP_PIXEL(7)
-#undef DBOT_SWEEP_PIXEL
-                x0 += o_e0r; x1 += o_e1r; x2 += o_e2r;
-                fr = dbot_add(fr, 1.0f);
-                trow += 4u * (uint32_t)ww;
-            }
+            const uint32_t w = __shfl_sync(DBOT_FULL, word, qb >> 5);
+            const int pre = __shfl_sync(DBOT_FULL, wpre, qb >> 5);
+            /* triangles hold their lanes in order and every one of them has at least one row, so the
+             * owner of unit q is the number of first-row bits at or below q, minus one */
+            const int owner = min(pre + __popc(w & le) - 1, 31);
+            const int opa = __shfl_sync(DBOT_FULL, pa, owner);
+            dbot_span_unit(rec_s + 4u * DBOT_REC_WORDS * (uint32_t)owner, q - (opa & 0x7ff), opa >> 11, q < H, tile_s,
+                           row0, col0, ww);
         }
-        __syncwarp();
-
-        unsigned m = __ballot_sync(DBOT_FULL, big);
-        while (m)
-        {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            dbot_tri q;
-            q.Xa = __shfl_sync(DBOT_FULL, s.Xa, j); q.Ya = __shfl_sync(DBOT_FULL, s.Ya, j);
-            q.Xb = __shfl_sync(DBOT_FULL, s.Xb, j); q.Yb = __shfl_sync(DBOT_FULL, s.Yb, j);
-            q.Xc = __shfl_sync(DBOT_FULL, s.Xc, j); q.Yc = __shfl_sync(DBOT_FULL, s.Yc, j);
-            q.cmin = __shfl_sync(DBOT_FULL, s.cmin, j); q.cmax = __shfl_sync(DBOT_FULL, s.cmax, j);
-            q.rmin = __shfl_sync(DBOT_FULL, s.rmin, j); q.rmax = __shfl_sync(DBOT_FULL, s.rmax, j);
-            q.flip = __shfl_sync(DBOT_FULL, s.flip, j);
-            q.small = 0;
-            q.clipped = 0;
-            q.m0 = __shfl_sync(DBOT_FULL, s.m0, j); q.m1 = __shfl_sync(DBOT_FULL, s.m1, j);
-            q.m2 = __shfl_sync(DBOT_FULL, s.m2, j);
-            q.wlo = __shfl_sync(DBOT_FULL, s.wlo, j); q.whi = __shfl_sync(DBOT_FULL, s.whi, j);
-            const int dc = lane & 7, dr = lane >> 3;
-            for (int r0 = q.rmin; r0 <= q.rmax; r0 += 4)
-            {
-                const int r = r0 + dr;
-                for (int c0 = q.cmin; c0 <= q.cmax; c0 += 8)
-                {
-                    const int c = c0 + dc;
-                    if (r <= q.rmax && c <= q.cmax && dbot_covers(q, c, r))
-                        dbot_zmax(s_wt + (r - row0) * ww + (c - col0),
-                                  dbot_fragment_w(q, (float)c, (float)r));
-                }
-            }
-        }
-        __syncwarp();
+        __syncwarp(); /* the record buffer is rewritten by the next batch */
     }
 }
 
@@ -216,8 +267,8 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
     __shared__ __align__(8) uint64_t s_bar;      /* TMA mesh staging */
     __shared__ int s_bb[4];
     __shared__ int s_cbb[DBOT_BOX_CHUNKS][4]; /* snapped box of each mesh chunk (multi-chunk meshes) */
-    __shared__ int s_batch;                      /* next triangle batch of the current raster pass */
-    __shared__ unsigned char s_owner_all[DBOT_CW][DBOT_OWNER_CAP]; /* block -> owning lane, per warp */
+    __shared__ int s_cnt[4];                     /* raster pass: survivors, tall + wide, next batch */
+    __shared__ uint32_t s_mask[DBOT_CW][32];     /* first-row masks of the span batches, per warp */
     __shared__ double s_red[DBOT_CW];
 
     const int tid = threadIdx.x;
@@ -317,10 +368,24 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
     if (MODE == DBOT_MODE_UPDATE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DBOT_COMPUTE_REGS));
     uint16_t* s_tri = (uint16_t*)(smem + p.off_tri);
     float4* s_v4 = (float4*)(smem + p.off_v4);
-    int* s_Y = (int*)(smem + p.off_Y);
+    int2* s_XY = (int2*)(smem + p.off_XY);
     uint32_t* s_wt = (uint32_t*)(smem + p.off_wt);
+    dbot_raster_smem S;
+    S.tri = s_tri;
+    S.v4 = s_v4;
+    S.XY = s_XY;
+    S.list = (uint16_t*)(smem + p.off_list);
+    S.rec = (uint32_t*)(smem + p.off_rec) + 32 * DBOT_REC_WORDS * warp;
+    S.mask = s_mask[warp];
+    S.wt = s_wt;
+    S.counters = s_cnt;
     uint32_t parity = 0;
     int staged = -1;
+    /* the tile starts empty and every mixture pass hands it back empty (it clears what it reads) */
+    {
+        uint4* w4 = reinterpret_cast<uint4*>(s_wt);
+        for (int q = tid; q < (int)(p.wcap >> 2); q += DBOT_CT) w4[q] = make_uint4(0u, 0u, 0u, 0u);
+    }
 
     /* TMA-stage the triangle list of one mesh chunk: one thread arms the mbarrier with the
      * byte count and issues the bulk copy; every compute thread waits on the barrier phase. */
@@ -348,8 +413,8 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
         {
             const float4 o = __ldg(vg + v);
             const dbot_vertex t = dbot_transform_vertex(o.x, o.y, o.z, pose, p.K);
-            s_v4[v] = make_float4(t.x, t.y, t.z, __int_as_float(t.X));
-            s_Y[v] = t.Y;
+            s_v4[v] = make_float4(t.x, t.y, t.z, t.iz);
+            s_XY[v] = make_int2(t.X, t.Y);
             if (t.X != DBOT_VERT_INVALID)
             {
                 mnx = min(mnx, t.X); mxx = max(mxx, t.X);
@@ -499,20 +564,16 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                 const int rb1 = min(rb0 + tile_rows - 1, r1);
                 const int c0 = cb0, c1 = min(cb0 + tile_cols - 1, wc1), ww = c1 - c0 + 1; /* this tile */
                 const int npx = (rb1 - rb0 + 1) * ww;
-                compute_sync(); /* previous band's readers of the tile are done */
-                {
-                    uint4* w4 = reinterpret_cast<uint4*>(s_wt);
-                    const int n4 = (npx + 3) >> 2; /* wcap is a multiple of 4 */
-                    for (int q = tid; q < n4; q += DBOT_CT) w4[q] = make_uint4(0u, 0u, 0u, 0u);
-                }
                 if (!MULTI)
                 {
                     stage_chunk(0); /* resident after the first particle */
-                    if (tid == 0) s_batch = 0;
+                    if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; }
+                    compute_sync(); /* counters published; every warp is done with the previous tile */
+                    DBOT_TL();
+                    dbot_raster_prepass(S, p.chunks[0].n_tris, p.chunks[0].cull_sign, rb0, rb1, c0, c1, tid);
                     compute_sync();
-                    DBOT_TL(); /* tile cleared */
-                    dbot_raster_chunk(s_tri, p.chunks[0].n_tris, s_v4, s_Y, p.K, s_wt, s_owner_all[warp],
-                                      &s_batch, rb0, rb1, c0, c1, lane);
+                    DBOT_TL(); /* prepass done */
+                    dbot_raster_sweep(S, p.chunks[0].n_tris, p.K, rb0, rb1, c0, c1, lane);
                     DBOT_TL(); /* this warp's raster done */
                 }
                 else
@@ -526,14 +587,15 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                                 dbot_ceil_subpix(b2) > rb1 || dbot_floor_subpix(b3) < rb0)
                                 continue;
                         }
-                        stage_chunk(c); /* leading barrier orders tile init / previous raster */
+                        stage_chunk(c); /* leading barrier orders the previous raster / mixture pass */
                         const dbot_chunk ch = p.chunks[c];
                         int d0 = INT_MAX, d1 = INT_MIN, d2 = INT_MAX, d3 = INT_MIN;
                         transform_chunk(ch, pose + 12 * ch.obj, d0, d1, d2, d3);
-                        if (tid == 0) s_batch = 0;
+                        if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; }
                         compute_sync();
-                        dbot_raster_chunk(s_tri, ch.n_tris, s_v4, s_Y, p.K, s_wt, s_owner_all[warp],
-                                          &s_batch, rb0, rb1, c0, c1, lane);
+                        dbot_raster_prepass(S, ch.n_tris, ch.cull_sign, rb0, rb1, c0, c1, tid);
+                        compute_sync();
+                        dbot_raster_sweep(S, ch.n_tris, p.K, rb0, rb1, c0, c1, lane);
                     }
                 }
                 compute_sync();
@@ -544,8 +606,11 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                 {
                     for (int r = rb0 + warp; r <= rb1; r += DBOT_CW)
                         for (int cc = lane; cc < ww; cc += 32)
+                        {
                             p.depth_out[(size_t)r * p.cols + c0 + cc] =
                                 dbot_depth_from_w(s_wt[(r - rb0) * ww + cc]);
+                            s_wt[(r - rb0) * ww + cc] = DBOT_W_EMPTY;
+                        }
                 }
                 else
                 {
@@ -557,7 +622,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                         size_t g; /* element offset of the unit's first column in the state / table */
                     };
                     auto fetch = [&](int r, int cb, unit& u) {
-                        const uint32_t* wrow = s_wt + (r - rb0) * ww + cb + lane;
+                        uint32_t* wrow = s_wt + (r - rb0) * ww + cb + lane;
                         u.g = (size_t)r * p.pitch + c0 + cb + lane;
 #pragma unroll
                         for (int j = 0; j < DBOT_UNIT_PX; ++j)
@@ -566,6 +631,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                         for (int j = 0; j < DBOT_UNIT_PX; ++j)
                             if (u.wb[j] != DBOT_W_EMPTY)
                             {
+                                wrow[32 * j] = DBOT_W_EMPTY; /* hand the tile back empty */
                                 u.tab[j] = __ldg(p.tab + u.g + 32 * j);
                                 /* update launches may read a slot whose covered pixels were written
                                  * in an earlier launch phase by its adopter-to-be: L2-coherent, not .nc */
@@ -621,10 +687,10 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
 #ifdef DBOT_DBG_TIMELINE
                 DBOT_TL();
                 if (blockIdx.x == 3 && k >= 3 * (int)gridDim.x && k < 5 * (int)gridDim.x)
-                    printf("mode %d particle %d cycles: transform+window %lld clear %lld raster(w0) %lld "
+                    printf("mode %d particle %d cycles: transform+window %lld sync %lld prepass %lld raster(w0) %lld "
                            "mixture(w0, incl. wait for other warps' raster) %lld reduce %lld total %lld\n",
                            MODE, i, tl[1] - tl[0], tl[2] - tl[1], tl[3] - tl[2], tl[4] - tl[3], tl[5] - tl[4],
-                           tl[5] - tl[0]);
+                           tl[6] - tl[5], tl[6] - tl[0]);
 #endif
                 if (MODE == DBOT_MODE_UPDATE)
                 {

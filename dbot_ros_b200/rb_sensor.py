@@ -63,6 +63,9 @@ class Parameters:
     vertex_shader_file: str = ""
     fragment_shader_file: str = ""
     geometry_shader_file: str = "none"
+    # B200 extension (optional YAML key gpu/cull_backfaces, default true): skip triangles facing away
+    # from the camera for meshes proven closed; false = draw every triangle as dbot's renderer does
+    cull_backfaces: bool = True
 
     @classmethod
     def from_dict(cls, tree):
@@ -86,6 +89,7 @@ class Parameters:
         p.vertex_shader_file = str(gpu.get("vertex_shader_file", ""))
         p.fragment_shader_file = str(gpu.get("fragment_shader_file", ""))
         p.geometry_shader_file = str(gpu.get("geometry_shader_file", "none"))
+        p.cull_backfaces = bool(gpu.get("cull_backfaces", True))
         return p
 
     @classmethod
@@ -225,7 +229,8 @@ class B200KinectImageModel(RbSensor):
             max_depth=MAX_DEPTH, p_occluded_visible=params.occlusion.p_occluded_visible,
             p_occluded_occluded=params.occlusion.p_occluded_occluded,
             initial_occlusion_prob=params.occlusion.initial_occlusion_prob,
-            delta_time=params.delta_time, device_id=device_id, occlusion_mode=occlusion_mode)
+            delta_time=params.delta_time, device_id=device_id, occlusion_mode=occlusion_mode,
+            cull_backfaces=0 if getattr(params, "cull_backfaces", True) else 1)
         abi.check(self._lib, self._lib.dbot_b200_create(C.byref(cfg), C.byref(self._h)))
         # RbSensor::default_poses_ -- one PoseVector (position, euler vector) per object
         self._default_poses = np.zeros((self.n_objects, 6))
@@ -310,6 +315,10 @@ class B200KinectImageModel(RbSensor):
     @property
     def n_slots(self):
         return self._lib.dbot_b200_n_slots(self._h)
+
+    def cull_sign(self, obj):
+        """+1 / -1: back faces of this object are skipped (mesh proven closed); 0: all triangles drawn"""
+        return self._lib.dbot_b200_cull_sign(self._h, int(obj))
 
     @property
     def free_slots(self):

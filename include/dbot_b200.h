@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DBOT_B200_ABI_VERSION 1
+#define DBOT_B200_ABI_VERSION 2
 #define DBOT_B200_MAX_OBJECTS 8
 
 typedef struct dbot_b200_sensor dbot_b200_sensor; /* opaque */
@@ -60,6 +60,12 @@ typedef struct
     int32_t occlusion_mode; /* 0 = dense: one full-frame fp32 occlusion image per particle with the
                                semantics of dbot's GPU evaluator (whole image propagated on every
                                update).  Other values are reserved. */
+    int32_t cull_backfaces; /* 0 = triangles facing away from the camera are skipped for every object whose
+                               mesh is proven closed and consistently oriented (dbot_b200_cull_sign != 0;
+                               the nearest surface of such a mesh is always camera-facing, so the rendered
+                               depth is unchanged); 1 = never: every triangle is drawn, as dbot's
+                               RigidBodyRenderer does.  Open or inconsistently oriented meshes are always
+                               drawn completely. */
 } dbot_b200_config;
 
 /* RbSensorBuilder<State>::build() with use_gpu == true */
@@ -131,6 +137,9 @@ int dbot_b200_filter_track(dbot_b200_filter* f, const float* depth_m, double* ou
 
 /* ---- state read-back (tests, debugging) ---- */
 int dbot_b200_n_slots(dbot_b200_sensor* s);
+/* back-face culling decision for one object: +1 / -1 = the sign of the snapped screen-space area of the
+ * triangles that are drawn, 0 = all triangles are drawn */
+int dbot_b200_cull_sign(dbot_b200_sensor* s, int32_t object);
 double dbot_b200_observation_time(dbot_b200_sensor* s);
 /* physical occlusion slots not in use (pool of 2*max_particles; n_slots + free == pool size) */
 int dbot_b200_free_slot_count(dbot_b200_sensor* s);

@@ -36,6 +36,7 @@ struct oracle_sensor
     int32_t** tris;
     int* n_tris;
     int max_verts;
+    int* cull_sign;  /* per object, see oracle_cull_sign */
     /* pixel model constants */
     double lambda, wD, c, log_c;
     /* state */
@@ -175,6 +176,7 @@ static void raster_object(const oracle_sensor* s, int o, const vert_scratch* vs,
         int64_t area2 = (int64_t)(Xb - Xa) * (int64_t)(Yc - Ya) - (int64_t)(Yb - Ya) * (int64_t)(Xc - Xa);
         if (area2 == 0) continue;
         int64_t sgn = area2 > 0 ? 1 : -1;
+        if (s->cfg.cull_backfaces && s->cull_sign[o] != 0 && sgn != s->cull_sign[o]) continue;
 
         int32_t cmin = ceil_div_subpix(imin3(Xa, Xb, Xc));
         int32_t cmax = floor_div_subpix(imax3(Xa, Xb, Xc));
@@ -253,6 +255,95 @@ static void free_scratch(vert_scratch* vs)
 }
 
 /* ------------------------------------------------------------------------- */
+/* Closed-mesh proof for back-face culling (NOT in upstream dbot, whose renderer draws every
+ * triangle; new-build decision documented in DESIGN.md).  Vertices with bit-identical
+ * positions are welded (meshes exported with per-face vertices are still closed surfaces);
+ * the mesh is closed and consistently oriented when every directed edge u->v occurs once and
+ * its opposite v->u occurs once.  The orientation of each connected component is the sign of
+ * its signed volume; all components must agree.  Outward-oriented (counter-clockwise seen from
+ * outside, positive volume) triangles that face the camera project to negative area in an
+ * image whose x grows to the right and y downwards (fx fy > 0). */
+typedef struct { int32_t u, v, tri; } dedge;
+static int cmp_dedge(const void* a, const void* b)
+{
+    const dedge* x = (const dedge*)a; const dedge* y = (const dedge*)b;
+    if (x->u != y->u) return x->u < y->u ? -1 : 1;
+    if (x->v != y->v) return x->v < y->v ? -1 : 1;
+    return 0;
+}
+static const float* g_weld_v; /* qsort context (oracle_create is not re-entrant; test infrastructure) */
+static int cmp_weld(const void* a, const void* b)
+{
+    return memcmp(g_weld_v + 3 * *(const int32_t*)a, g_weld_v + 3 * *(const int32_t*)b, 3 * sizeof(float));
+}
+static int32_t uf_find(int32_t* p, int32_t i)
+{
+    while (p[i] != i) { p[i] = p[p[i]]; i = p[i]; }
+    return i;
+}
+static int compute_cull_sign(const float* V, int nv, const int32_t* T, int nt, double fxfy)
+{
+    if (nt < 4 || nv < 4) return 0;
+    int result = 0;
+    int32_t* order = (int32_t*)malloc(sizeof(int32_t) * nv);
+    int32_t* canon = (int32_t*)malloc(sizeof(int32_t) * nv);
+    dedge* E = (dedge*)malloc(sizeof(dedge) * 3 * (size_t)nt);
+    int32_t* comp = (int32_t*)malloc(sizeof(int32_t) * nt);
+    double* vol = (double*)calloc((size_t)nt, sizeof(double));
+    if (!order || !canon || !E || !comp || !vol) goto done;
+    for (int i = 0; i < nv; ++i) order[i] = i;
+    g_weld_v = V;
+    qsort(order, nv, sizeof(int32_t), cmp_weld);
+    for (int i = 0; i < nv; ++i)
+        canon[order[i]] = (i > 0 && cmp_weld(&order[i], &order[i - 1]) == 0) ? canon[order[i - 1]] : order[i];
+    for (int t = 0; t < nt; ++t)
+    {
+        int32_t a = canon[T[3 * t]], b = canon[T[3 * t + 1]], c = canon[T[3 * t + 2]];
+        if (a == b || b == c || c == a) goto done; /* collapsed triangle: not provably closed */
+        E[3 * t] = (dedge){a, b, t}; E[3 * t + 1] = (dedge){b, c, t}; E[3 * t + 2] = (dedge){c, a, t};
+        comp[t] = t;
+    }
+    qsort(E, 3 * (size_t)nt, sizeof(dedge), cmp_dedge);
+    for (size_t i = 1; i < 3 * (size_t)nt; ++i)
+        if (cmp_dedge(&E[i], &E[i - 1]) == 0) goto done; /* a directed edge used twice */
+    for (size_t i = 0; i < 3 * (size_t)nt; ++i)
+    {
+        dedge key = {E[i].v, E[i].u, 0};
+        const dedge* m = (const dedge*)bsearch(&key, E, 3 * (size_t)nt, sizeof(dedge), cmp_dedge);
+        if (!m) goto done; /* boundary edge: open mesh */
+        int32_t ra = uf_find(comp, E[i].tri), rb = uf_find(comp, m->tri);
+        if (ra != rb) comp[ra] = rb;
+    }
+    for (int t = 0; t < nt; ++t)
+    {
+        const float* a = V + 3 * T[3 * t]; const float* b = V + 3 * T[3 * t + 1]; const float* c = V + 3 * T[3 * t + 2];
+        double cx = (double)b[1] * c[2] - (double)b[2] * c[1];
+        double cy = (double)b[2] * c[0] - (double)b[0] * c[2];
+        double cz = (double)b[0] * c[1] - (double)b[1] * c[0];
+        vol[uf_find(comp, t)] += a[0] * cx + a[1] * cy + a[2] * cz;
+    }
+    {
+        int sgn = 0;
+        for (int t = 0; t < nt; ++t)
+        {
+            if (uf_find(comp, t) != t) continue;
+            int sv = vol[t] > 0.0 ? 1 : (vol[t] < 0.0 ? -1 : 0);
+            if (sv == 0 || (sgn != 0 && sv != sgn)) goto done;
+            sgn = sv;
+        }
+        result = (fxfy > 0.0) ? -sgn : sgn;
+    }
+done:
+    free(order); free(canon); free(E); free(comp); free(vol);
+    return result;
+}
+
+int oracle_cull_sign(const oracle_sensor* s, int32_t o)
+{
+    return (s && o >= 0 && o < s->n_obj) ? s->cull_sign[o] : 0;
+}
+
+/* ------------------------------------------------------------------------- */
 int oracle_create(const oracle_config* cfg, oracle_sensor** out)
 {
     if (!cfg || !out) return -1;
@@ -277,6 +368,7 @@ int oracle_create(const oracle_config* cfg, oracle_sensor** out)
     s->tris = (int32_t**)calloc(s->n_obj, sizeof(int32_t*));
     s->n_verts = (int*)calloc(s->n_obj, sizeof(int));
     s->n_tris = (int*)calloc(s->n_obj, sizeof(int));
+    s->cull_sign = (int*)calloc(s->n_obj, sizeof(int));
     for (int o = 0; o < s->n_obj; ++o)
     {
         int nv = cfg->n_vertices[o], nt = cfg->n_triangles[o];
@@ -290,6 +382,7 @@ int oracle_create(const oracle_config* cfg, oracle_sensor** out)
         memcpy(s->tris[o], cfg->triangles[o], sizeof(int32_t) * 3 * nt);
         for (int i = 0; i < 3 * nt; ++i)
             if (s->tris[o][i] < 0 || s->tris[o][i] >= nv) return -6;
+        s->cull_sign[o] = compute_cull_sign(s->verts[o], nv, s->tris[o], nt, fx * fy);
     }
     s->cfg.vertices = NULL; s->cfg.triangles = NULL; s->cfg.n_vertices = NULL; s->cfg.n_triangles = NULL;
     /* dbot KinectPixelModel: exponential_rate = -log(0.5)/half_life_depth */
@@ -307,7 +400,7 @@ int oracle_destroy(oracle_sensor* s)
 {
     if (!s) return -1;
     for (int o = 0; o < s->n_obj; ++o) { free(s->verts[o]); free(s->tris[o]); }
-    free(s->verts); free(s->tris); free(s->n_verts); free(s->n_tris);
+    free(s->verts); free(s->tris); free(s->n_verts); free(s->n_tris); free(s->cull_sign);
     free(s->occ); free(s->occ_time); free(s->obs);
     free(s);
     return 0;

@@ -56,6 +56,14 @@ typedef struct
     /* 1: round p_vis*(1-o), p_occ*o, p_inf and o to float before the log, as
        the dbot CPU model's `float` locals do (soft detail). */
     int32_t float_intermediates;
+    /* 0: every triangle is rasterised, as upstream (dbot's renderer does not cull).
+       1: triangles facing away from the camera are skipped for every object whose mesh is
+          proven closed and consistently oriented (oracle_cull_sign != 0) -- the rule the CUDA
+          library applies by default.  For such a mesh the nearest surface along any ray from
+          outside is camera-facing, so the rendered depth is the same except where rounding
+          decides between the two triangles that meet at a silhouette edge
+          (tests/test_oracle_known_answers.py counts those pixels). */
+    int32_t cull_backfaces;
 } oracle_config;
 
 int oracle_create(const oracle_config* cfg, oracle_sensor** out);
@@ -84,6 +92,12 @@ double oracle_p_visible(const oracle_sensor* s, double y, double d);
 double oracle_p_occluded(const oracle_sensor* s, double y, double d);
 double oracle_p_occluded_inf(const oracle_sensor* s, double y);
 double oracle_propagate(const oracle_sensor* s, double o, double dt);
+
+/* sign of the snapped screen-space area (x right, y down) of the camera-facing triangles of
+   object o: +1 / -1 when its mesh is closed (every directed edge of the position-welded mesh
+   is matched by exactly one opposite edge) with every connected component oriented the same
+   way, 0 otherwise.  Independent of cull_backfaces. */
+int oracle_cull_sign(const oracle_sensor* s, int32_t o);
 
 /* test support: append a slot exported from another instance (see dbot_oracle.c) */
 int oracle_import_slot(oracle_sensor* s, const float* occ, const double* occ_time);

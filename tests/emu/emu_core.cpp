@@ -30,6 +30,9 @@ struct emu_config
     double tail_weight, model_sigma, sigma_factor, half_life_depth, max_depth;
     double p_occluded_visible, p_occluded_occluded;
     int32_t zcap; /* z tile capacity in pixels: small values force the multi-band path */
+    int32_t cull_sign[8]; /* per object: sign of the snapped area of the triangles that are kept, 0 = all */
+    int32_t force_blocks; /* 1: every triangle through the int64 block walk (dbot_covers), as the
+                             kernel does for DBOT_TRI_WIDE triangles */
 };
 
 /* observation table exactly as dbot_observation_kernel computes it */
@@ -128,17 +131,46 @@ double emu_particle(const emu_config* cfg, const float* pose, const float* tab, 
                 for (int t = 0; t < cfg->n_triangles[o]; ++t)
                 {
                     const int32_t* tri = cfg->triangles[o] + 3 * t;
-                    dbot_tri s;
-                    if (!dbot_setup_triangle(tv[tri[0]], tv[tri[1]], tv[tri[2]], K, rb0, rb1, c0, c1, s))
+                    const dbot_vertex &va = tv[tri[0]], &vb = tv[tri[1]], &vc = tv[tri[2]];
+                    int cmin, cmax, rmin, rmax;
+                    int kind = dbot_prepass_triangle(va.X, va.Y, vb.X, vb.Y, vc.X, vc.Y, cfg->cull_sign[o],
+                                                     rb0, rb1, c0, c1, cmin, cmax, rmin, rmax);
+                    if (kind == DBOT_TRI_REJECT) continue;
+                    if (kind == DBOT_TRI_WIDE || cfg->force_blocks)
+                    {
+                        dbot_tri s;
+                        if (!dbot_setup_triangle(va, vb, vc, K, rb0, rb1, c0, c1, s)) continue;
+                        for (int r = s.rmin; r <= s.rmax; ++r)
+                            for (int c = s.cmin; c <= s.cmax; ++c)
+                                if (dbot_covers(s, c, r))
+                                {
+                                    const uint32_t w = dbot_fragment_w(s, (float)c, (float)r);
+                                    uint32_t* dst = &wt[(size_t)(r - rb0) * ww + (c - c0)];
+                                    if (w > *dst) *dst = w;
+                                }
                         continue;
-                    for (int r = s.rmin; r <= s.rmax; ++r)
-                        for (int c = s.cmin; c <= s.cmax; ++c)
-                            if (dbot_covers(s, c, r))
-                            {
-                                const uint32_t w = dbot_fragment_w(s, (float)c, (float)r);
-                                uint32_t* dst = &wt[(size_t)(r - rb0) * ww + (c - c0)];
-                                if (w > *dst) *dst = w;
-                            }
+                    }
+                    /* (triangle, row) span units, as the kernel's lanes walk them */
+                    dbot_span_rec s;
+                    dbot_setup_spans(va, vb, vc, K, cmin, cmax, rmin, rmax, s);
+                    const int co = s.org & 0xffff, ro = s.org >> 16;
+                    const int bwm1 = s.aux & 0xff, split = (s.aux >> 8) & 0xff, long_left = (s.aux >> 16) & 1;
+                    for (int j = 0; j <= rmax - rmin; ++j)
+                    {
+                        const dbot_edge& B = j >= split ? s.B2 : s.B1;
+                        int first;
+                        const int n = long_left ? dbot_row_span(s.A, B, j, bwm1, first)
+                                                : dbot_row_span(B, s.A, j, bwm1, first);
+                        const int r = ro + j;
+                        const float wr = dbot_fmaf(s.m1, (float)r, s.m2);
+                        for (int k = 0; k < n; ++k)
+                        {
+                            const int c = co + first + k;
+                            const uint32_t w = dbot_span_w(s, (float)c, wr);
+                            uint32_t* dst = &wt[(size_t)(r - rb0) * ww + (c - c0)];
+                            if (w > *dst) *dst = w;
+                        }
+                    }
                 }
             }
             float facc = 0.f; /* the kernel accumulates float partials per thread */
@@ -161,6 +193,49 @@ double emu_particle(const emu_config* cfg, const float* pose, const float* tab, 
         }
     }
     return acc;
+}
+
+/* coverage of one snapped triangle inside rows [row0,row1] x columns [col0,col1], two ways: the
+ * span units (dbot_setup_spans + dbot_row_span) and the direct int64 edge functions
+ * (dbot_covers).  Returns the number of pixels on which they disagree (-1: the triangle is not
+ * one the span units take); *n_cov receives the number of covered pixels. */
+int emu_span_mismatches(const int32_t* XY /* Xa Ya Xb Yb Xc Yc */, int row0, int row1, int col0, int col1,
+                        int32_t* n_cov)
+{
+    dbot_vertex v[3];
+    for (int k = 0; k < 3; ++k)
+    {
+        v[k].x = (float)k; v[k].y = (float)(k * k); v[k].z = 1.0f + k; v[k].iz = 1.0f / v[k].z;
+        v[k].X = XY[2 * k]; v[k].Y = XY[2 * k + 1];
+    }
+    int cmin, cmax, rmin, rmax;
+    *n_cov = 0;
+    const int kind = dbot_prepass_triangle(v[0].X, v[0].Y, v[1].X, v[1].Y, v[2].X, v[2].Y, 0, row0, row1, col0,
+                                           col1, cmin, cmax, rmin, rmax);
+    if (kind != DBOT_TRI_SPANS && kind != DBOT_TRI_TALL) return -1;
+    dbot_camera K = {1.f, 0.f, 0.f, 1.f, 0.f, 1.f, 0.f, 0.f, 1.f, 0.f};
+    dbot_tri t;
+    t.Xa = v[0].X; t.Ya = v[0].Y; t.Xb = v[1].X; t.Yb = v[1].Y; t.Xc = v[2].X; t.Yc = v[2].Y;
+    const long long a2 = (long long)(t.Xb - t.Xa) * (t.Yc - t.Ya) - (long long)(t.Yb - t.Ya) * (t.Xc - t.Xa);
+    t.flip = a2 < 0;
+    dbot_span_rec s;
+    dbot_setup_spans(v[0], v[1], v[2], K, cmin, cmax, rmin, rmax, s);
+    const int bwm1 = s.aux & 0xff, split = (s.aux >> 8) & 0xff, long_left = (s.aux >> 16) & 1;
+    int bad = 0;
+    for (int j = 0; j <= rmax - rmin; ++j)
+    {
+        const dbot_edge& B = j >= split ? s.B2 : s.B1;
+        int first;
+        const int n = long_left ? dbot_row_span(s.A, B, j, bwm1, first) : dbot_row_span(B, s.A, j, bwm1, first);
+        for (int i = 0; i <= cmax - cmin; ++i)
+        {
+            const bool in_span = n > 0 && i >= first && i < first + n;
+            const bool cov = dbot_covers(t, cmin + i, rmin + j);
+            bad += in_span != cov;
+            *n_cov += cov;
+        }
+    }
+    return bad;
 }
 
 /* the scalar mixture term alone, for tests/test_pixel_math.py */

@@ -48,7 +48,7 @@ class OracleConfig(C.Structure):
         ("half_life_depth", C.c_double), ("max_depth", C.c_double),
         ("p_occluded_visible", C.c_double), ("p_occluded_occluded", C.c_double),
         ("initial_occlusion_prob", C.c_double), ("delta_time", C.c_double),
-        ("eager", C.c_int32), ("float_intermediates", C.c_int32),
+        ("eager", C.c_int32), ("float_intermediates", C.c_int32), ("cull_backfaces", C.c_int32),
     ]
 
 
@@ -61,6 +61,8 @@ class EmuConfig(C.Structure):
         ("half_life_depth", C.c_double), ("max_depth", C.c_double),
         ("p_occluded_visible", C.c_double), ("p_occluded_occluded", C.c_double),
         ("zcap", C.c_int32),
+        ("cull_sign", C.c_int32 * 8),   # per object: 0 = keep both orientations
+        ("force_blocks", C.c_int32),    # 1: every triangle through the int64 block walk (dbot_covers)
     ]
 
 
@@ -87,6 +89,7 @@ def oracle_lib():
         lib.oracle_import_slot.argtypes = [P, P, P]
         lib.oracle_set_num_threads.argtypes = [C.c_int]
         lib.oracle_get_max_threads.restype = C.c_int
+        lib.oracle_cull_sign.argtypes = [P, C.c_int32]
         for f in ("oracle_p_visible", "oracle_p_occluded", "oracle_propagate"):
             getattr(lib, f).argtypes = [P, C.c_double, C.c_double]
             getattr(lib, f).restype = C.c_double
@@ -107,6 +110,7 @@ def emu_lib():
         lib.emu_pixel_term.argtypes = [C.POINTER(EmuConfig), C.c_float, C.c_float, C.c_float,
                                        C.c_float, C.c_float, C.POINTER(C.c_float)]
         lib.emu_pixel_term.restype = C.c_float
+        lib.emu_span_mismatches.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
         _emu = lib
     return _emu
 
@@ -114,13 +118,15 @@ def emu_lib():
 class Oracle:
     """oracle_* behind the same method names as dbot_ros_b200.B200KinectImageModel"""
 
-    def __init__(self, rows, cols, K, vertices, triangles, params, eager=1, float_intermediates=0):
+    def __init__(self, rows, cols, K, vertices, triangles, params, eager=1, float_intermediates=0,
+                 cull=0):
         self.lib = oracle_lib()
         self.rows, self.cols, self.n_objects = rows, cols, len(vertices)
         cfg, self._keep = abi.make_config(rows, cols, K, 0, vertices, triangles, struct=OracleConfig,
                                           **params)
         cfg.eager = eager
         cfg.float_intermediates = float_intermediates
+        cfg.cull_backfaces = cull
         self.h = C.c_void_p()
         rc = self.lib.oracle_create(C.byref(cfg), C.byref(self.h))
         if rc:
@@ -150,6 +156,9 @@ class Oracle:
         out = np.empty(self.rows * self.cols, dtype=np.float32)
         assert self.lib.oracle_render(self.h, abi.ptr(pose), abi.ptr(out)) == 0
         return out.reshape(self.rows, self.cols)
+
+    def cull_sign(self, obj):
+        return self.lib.oracle_cull_sign(self.h, obj)
 
     @property
     def n_slots(self):
@@ -203,12 +212,16 @@ class Oracle:
 class Emu:
     """one-particle host walk through the kernel's phase functions (tests/emu/emu_core.cpp)"""
 
-    def __init__(self, rows, cols, K, vertices, triangles, params, zcap=1 << 20):
+    def __init__(self, rows, cols, K, vertices, triangles, params, zcap=1 << 20, cull_sign=None,
+                 force_blocks=0):
         self.lib = emu_lib()
         self.rows, self.cols, self.n_objects = rows, cols, len(vertices)
         p = {k: v for k, v in params.items()}
         cfg, self._keep = abi.make_config(rows, cols, K, 0, vertices, triangles, struct=EmuConfig, **p)
         cfg.zcap = zcap
+        for o, sg in enumerate(cull_sign or []):
+            cfg.cull_sign[o] = sg
+        cfg.force_blocks = force_blocks
         self.cfg = cfg
         self.params = params
         self.tab = None

@@ -44,7 +44,7 @@ def test_every_declared_symbol_is_exported_and_typed():
         assert hasattr(lib, nm), "libdbot_b200.so does not export %s" % nm
         assert nm in abi.SIGNATURES, "abi.py has no signature for %s" % nm
     assert sorted(abi.SIGNATURES) == names  # and the stub binds nothing the header does not declare
-    assert lib.dbot_b200_abi_version() == 1
+    assert lib.dbot_b200_abi_version() == 2
 
 
 def test_no_cpp_symbols_leak_as_entry_points():

@@ -18,20 +18,25 @@ def rel_err(got, want):
     return np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0)) if len(want) else 0.0
 
 
-def make_pair(mesh, ds, max_n, K=None):
+def make_pair(mesh, ds, max_n, K=None, cull=True):
+    """cull=True: the library's default (back faces of meshes proven closed are skipped) against the
+    oracle with the same rule; cull=False: every triangle drawn on both sides, as upstream dbot."""
     rows, cols = synth.resolution(ds)
     K = synth.camera_matrix(ds) if K is None else K
     V, T = synth.mesh_set(mesh) if isinstance(mesh, str) else mesh
     sensor = RbSensorBuilder(ObjectModel(V, T), CameraData(K, rows, cols),
-                             Parameters(sample_count=max_n)).build()
-    orc = oracle_lib.Oracle(rows, cols, K, V, T, synth.default_parameters())
+                             Parameters(sample_count=max_n, cull_backfaces=cull)).build()
+    orc = oracle_lib.Oracle(rows, cols, K, V, T, synth.default_parameters(), cull=1 if cull else 0)
+    for o in range(len(V)):
+        assert sensor.cull_sign(o) == (orc.cull_sign(o) if cull else 0)
     return sensor, orc, rows, cols, len(V)
 
 
+@pytest.mark.parametrize("cull", [True, False])
 @pytest.mark.parametrize("mesh,ds", [("uvsphere480", 4), ("icosphere5k", 1), ("three20k", 2),
                                      ("ico80", 8)])
-def test_render_bit_exact(mesh, ds):
-    sensor, orc, rows, cols, n_obj = make_pair(mesh, ds, 8)
+def test_render_bit_exact(mesh, ds, cull):
+    sensor, orc, rows, cols, n_obj = make_pair(mesh, ds, 8, cull=cull)
     rng = np.random.default_rng(5)
     gt = synth.ground_truth_poses(n_obj, rng)
     for pose in synth.particle_poses(gt, 6, rng, sigma_t=0.03, sigma_r=0.5):
@@ -173,7 +178,7 @@ def test_odd_resolution_pitch():
     K = np.array([[70.0, 0.3, 41.0], [0, 71.0, 30.0], [0, 0, 1]])
     V, T = synth.mesh_set("ico80")
     sensor = RbSensorBuilder(ObjectModel(V, T), CameraData(K, rows, cols), Parameters(sample_count=8)).build()
-    orc = oracle_lib.Oracle(rows, cols, K, V, T, synth.default_parameters())
+    orc = oracle_lib.Oracle(rows, cols, K, V, T, synth.default_parameters(), cull=1)
     rng = np.random.default_rng(8)
     gt = [(synth.rodrigues([0.1, 0.2, 0.3]), np.array([0.01, 0.0, 0.6]))]
     frame = synth.make_frame(orc.render, gt, rows, cols, rng)
@@ -338,7 +343,7 @@ def test_lazy_propagation_rebase():
     prm = dict(synth.default_parameters(), delta_time=5.0)
     sensor = RbSensorBuilder(ObjectModel(V, T), CameraData(K, rows, cols),
                              Parameters(sample_count=n, delta_time=5.0)).build()
-    orc = oracle_lib.Oracle(rows, cols, K, V, T, prm)
+    orc = oracle_lib.Oracle(rows, cols, K, V, T, prm, cull=1)
     rng = np.random.default_rng(33)
     gt = synth.ground_truth_poses(1, rng)
     idx = np.zeros(n, dtype=np.int32)
@@ -382,7 +387,7 @@ def test_maximum_sizes_and_ragged_inputs():
     K = np.array([[1160.0, 0.0, 640.0], [0.0, 1160.0, 480.0], [0.0, 0.0, 1.0]])
     Vb, Tb = synth.mesh_set("icosphere5k")
     sensor = RbSensorBuilder(ObjectModel(Vb, Tb), CameraData(K, rows, cols), Parameters(sample_count=2)).build()
-    orc = oracle_lib.Oracle(rows, cols, K, Vb, Tb, synth.default_parameters())
+    orc = oracle_lib.Oracle(rows, cols, K, Vb, Tb, synth.default_parameters(), cull=1)
     gt = [(synth.rodrigues([0.2, 0.1, -0.3]), np.array([0.01, -0.02, 0.4]))]
     pose = synth.pack_pose(*gt[0])
     want = orc.render(pose)

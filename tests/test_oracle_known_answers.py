@@ -276,3 +276,73 @@ def test_renderer_against_an_independent_ray_caster():
         # interior pixels agree to float32 accuracy; a pixel on an edge between two facets may take
         # either facet's plane (the same point in exact arithmetic)
         assert np.percentile(rel, 99) < 2e-6 and rel.max() < 1e-3
+
+
+# ---- back-face culling (new-build decision, not in upstream dbot: DESIGN.md section 2) -------------
+def _cull_sign(V, T, K=None):
+    K = synth.camera_matrix(8) if K is None else K
+    o = oracle_lib.Oracle(60, 80, K, [np.asarray(V, np.float32)], [np.asarray(T, np.int32)], PRM)
+    return o.cull_sign(0)
+
+
+def test_closed_mesh_proof_decides_culling_per_mesh():
+    V, T = synth.icosphere(1)
+    assert _cull_sign(V, T) == -1                       # closed, outward: camera-facing area is negative
+    assert _cull_sign(V, T[:, ::-1]) == +1              # the same surface inside out
+    assert _cull_sign(V, T[:-1]) == 0                   # one triangle missing: open -> every triangle drawn
+    flipped = T.copy()
+    flipped[3] = flipped[3][::-1]
+    assert _cull_sign(V, flipped) == 0                  # one triangle wound the other way: not oriented
+    assert _cull_sign(V, np.vstack([T, T[:1]])) == 0    # a triangle twice: edge used twice in one direction
+    mirrored = synth.camera_matrix(8)
+    mirrored[0, 0] = -mirrored[0, 0]
+    assert _cull_sign(V, T, mirrored) == +1             # fx < 0 mirrors the image: the kept sign flips
+    # per-face vertices (every triangle its own three vertices, as many .obj exporters write them) are
+    # welded by position before the edges are matched
+    Vs = V[T].reshape(-1, 3)
+    Ts = np.arange(len(Vs), dtype=np.int32).reshape(-1, 3)
+    assert _cull_sign(Vs, Ts) == -1
+    # two separate closed shells with the same orientation; with opposite orientation no culling
+    V2 = np.vstack([V, V + np.float32(0.5)])
+    T2 = np.vstack([T, T + len(V)])
+    assert _cull_sign(V2, T2) == -1
+    assert _cull_sign(V2, np.vstack([T, T[:, ::-1] + len(V)])) == 0
+    # the multi-object meshes of the bench are all closed
+    for name in ("icosphere5k", "uvsphere480", "three20k"):
+        Vm, Tm = synth.mesh_set(name)
+        o = oracle_lib.Oracle(60, 80, synth.camera_matrix(8), Vm, Tm, PRM)
+        assert [o.cull_sign(i) for i in range(len(Vm))] == [-1] * len(Vm)
+
+
+def test_culled_render_differs_from_the_full_render_only_at_silhouette_ties():
+    """For a closed mesh the nearest surface is camera-facing, so skipping the other triangles must
+    leave the depth image unchanged -- except where rounding decides between the two triangles that
+    meet at a silhouette edge (both planes evaluated ~at the edge).  Quantified: at most a handful of
+    pixels per image (measured: 10 of 234 507), never a change of coverage, depth changes below
+    0.1 mm (measured: 37 micrometres; the sensor model's sigma is 3 mm)."""
+    rows, cols = synth.resolution(1)
+    K = synth.camera_matrix(1)
+    total_px = differing = 0
+    worst = 0.0
+    for name in ("icosphere5k", "three20k"):
+        V, T = synth.mesh_set(name)
+        full = oracle_lib.Oracle(rows, cols, K, V, T, PRM, cull=0)
+        culled = oracle_lib.Oracle(rows, cols, K, V, T, PRM, cull=1)
+        rng = synth.rng_for(7)
+        gt = synth.ground_truth_poses(len(V), rng)
+        frame = synth.make_frame(full.render, gt, rows, cols, rng)
+        poses = synth.particle_poses(gt, 6, rng, sigma_t=0.02, sigma_r=0.3)
+        for p in poses:
+            a, b = full.render(p), culled.render(p)
+            assert np.array_equal(np.isfinite(a), np.isfinite(b))      # same pixels covered
+            fin = np.isfinite(a)
+            total_px += int(fin.sum())
+            differing += int(np.sum(a[fin] != b[fin]))
+            worst = max(worst, float(np.max(np.abs(a[fin] - b[fin]))))
+        # and the log-weights agree far inside the parity tolerance
+        for o in (full, culled):
+            o.set_observation(frame)
+        la = full.loglikes_poses(poses, np.zeros(6, np.int32), False)
+        lb = culled.loglikes_poses(poses, np.zeros(6, np.int32), False)
+        assert np.max(np.abs(la - lb) / np.maximum(np.abs(la), 1.0)) < 1e-6
+    assert total_px > 100000 and differing <= total_px // 5000 and worst < 1e-4

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--parents", default="resampled", choices=["resampled", "identity", "few"],
                     help="parent pattern of the update calls: systematic resampling every frame, or none")
+    ap.add_argument("--nocull", action="store_true", help="draw every triangle (no back-face culling)")
     a = ap.parse_args()
     import torch
 
@@ -33,7 +34,7 @@ def main():
     n, rows, cols = w["n"], w["rows"], w["cols"]
     P = rows * cols
     sensor = RbSensorBuilder(ObjectModel(w["V"], w["T"]), CameraData(w["K"], rows, cols),
-                             Parameters(sample_count=n)).build()
+                             Parameters(sample_count=n, cull_backfaces=not a.nocull)).build()
     rng = synth.rng_for(a.config)
     gt = synth.ground_truth_poses(len(w["V"]), rng)
     frames = [synth.make_frame(sensor.render, gt, rows, cols, rng) for _ in range(2)]
@@ -70,7 +71,7 @@ def main():
         sensor.synchronize()
     prof = sensor.profile_read()
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-    out = {"config": a.config, "n": n, "parents": a.parents, "resolution": [cols, rows], "triangles": w["tris"],
+    out = {"config": a.config, "n": n, "parents": a.parents, "cull": not a.nocull, "resolution": [cols, rows], "triangles": w["tris"],
            "device_bytes": sensor.device_bytes}
     for mode, bytes_per in (("loglikes", None), ("update", 8.0 * P)):
         ms, cnt = prof[mode]
