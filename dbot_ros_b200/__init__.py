@@ -6,7 +6,7 @@ C-ABI in include/dbot_b200.h) and the host-side mirror of the reference's sensor
 works anywhere, but building a sensor needs libdbot_b200.so and a CUDA device.
 """
 from .abi import LIB_PATH, DbotB200Error, load_library  # noqa: F401
-from . import io, tracker  # noqa: F401
+from . import io, replay, tracker  # noqa: F401
 from .rb_sensor import (  # noqa: F401
     B200KinectImageModel,
     CameraData,

@@ -44,6 +44,9 @@ class Config(C.Structure):
         ("device_id", C.c_int32),
         ("occlusion_mode", C.c_int32),
         ("cull_backfaces", C.c_int32),
+        ("n_devices", C.c_int32),
+        ("device_ids", C.POINTER(C.c_int32)),
+        ("gather_mode", C.c_int32),
     ]
 
 
@@ -57,6 +60,8 @@ class FilterConfig(C.Structure):
         ("max_kl_divergence", C.c_double),
         ("seed", C.c_uint64),
         ("n_particles", C.c_int32),
+        ("moving_average_update_rate", C.c_double),
+        ("centers", (C.c_double * 3) * MAX_OBJECTS),
     ]
 
 
@@ -80,6 +85,9 @@ SIGNATURES = {
     "dbot_b200_filter_destroy": (C.c_int, [_P]),
     "dbot_b200_filter_initialize": (C.c_int, [_P, _P]),
     "dbot_b200_filter_track": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int32)]),
+    "dbot_b200_update_empty": (C.c_int, [_P]),
+    "dbot_b200_device_count": (C.c_int, [_P]),
+    "dbot_b200_migrated_slots": (C.c_int64, [_P]),
     "dbot_b200_n_slots": (C.c_int, [_P]),
     "dbot_b200_cull_sign": (C.c_int, [_P, C.c_int32]),
     "dbot_b200_observation_time": (C.c_double, [_P]),
@@ -127,7 +135,7 @@ def check(lib, rc):
 def make_config(rows, cols, K, max_particles, vertices, triangles, *, tail_weight, model_sigma,
                 sigma_factor, half_life_depth, max_depth, p_occluded_visible, p_occluded_occluded,
                 initial_occlusion_prob, delta_time, device_id=0, occlusion_mode=0,
-                cull_backfaces=0, struct=Config):
+                cull_backfaces=0, device_ids=None, gather_mode=0, struct=Config):
     """Fill a dbot_b200_config (or a layout-compatible struct).  Returns (cfg, keepalive)."""
     n_obj = len(vertices)
     v_arr = [np.ascontiguousarray(v, dtype=np.float32).reshape(-1, 3) for v in vertices]
@@ -163,9 +171,15 @@ def make_config(rows, cols, K, max_particles, vertices, triangles, *, tail_weigh
         cfg.device_id = int(device_id)
     if hasattr(cfg, "occlusion_mode"):
         cfg.occlusion_mode = int(occlusion_mode)
-    if hasattr(cfg, "cull_backfaces") and struct is Config:
+    ids = None
+    if struct is Config:
         cfg.cull_backfaces = int(cull_backfaces)
-    return cfg, (v_arr, t_arr, vp, tp, nv, nt)
+        cfg.gather_mode = int(gather_mode)
+        if device_ids is not None:
+            ids = (C.c_int32 * len(device_ids))(*[int(d) for d in device_ids])
+            cfg.n_devices = len(device_ids)
+            cfg.device_ids = C.cast(ids, C.POINTER(C.c_int32))
+    return cfg, (v_arr, t_arr, vp, tp, nv, nt, ids)
 
 
 def ptr(a):

@@ -95,6 +95,9 @@ struct dbot_kparams
     const float* poses;     /* [n][n_obj][12] */
     int32_t* indices;       /* [n] */
     double* out;            /* [n] */
+    double* peer_out[DBOT_B200_MAX_DEVICES]; /* fused gather: the same log-weight is also stored at
+                                                out_offset + i of every device's gathered vector (peer memory) */
+    int n_peers, out_offset;
     float* depth_out;       /* render: [rows*cols] */
     int* err_flag;
     /* shared-memory carve-up (bytes from the dynamic smem base) */
@@ -181,9 +184,37 @@ struct dbot_b200_sensor
     int64_t prof_launches[DBOT_B200_KERNEL_COUNT];
     int64_t launches;
     int64_t device_bytes;
+    int update_since_sync;   /* an update was enqueued through the device-pointer entry points */
+    int poisoned;            /* an update failed on the device: the slot tables are half-built, reset() required */
+    struct dbot_multi* multi; /* != nullptr: this handle shards its particles over several GPUs (multi_device.cuh) */
 };
+#define DBOT_CHECK_USABLE(s, what)                                                                          \
+    do                                                                                                      \
+    {                                                                                                       \
+        if ((s)->poisoned)                                                                                  \
+            return fail(-13, what ": an earlier update failed on the device and left the occlusion-slot "   \
+                             "tables half-built; call reset() first");                                      \
+    } while (0)
 
 static uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+/* multi_device.cuh */
+static int multi_create(const dbot_b200_config* cfg, dbot_b200_sensor* s);
+static int multi_destroy(dbot_b200_sensor* s);
+static int multi_set_observation(dbot_b200_sensor* s, const float* depth_m);
+static dbot_b200_sensor* multi_owner(dbot_b200_sensor* s, int32_t slot, int32_t* local);
+static int multi_timer_begin(dbot_b200_sensor* s);
+static int multi_timer_end(dbot_b200_sensor* s, float* out_ms);
+static int multi_n_slots(dbot_b200_sensor* s);
+static dbot_b200_sensor* multi_child(dbot_b200_sensor* s, int g);
+static int multi_count(dbot_b200_sensor* s);
+#define DBOT_SINGLE_ONLY(s, what)                                                                      \
+    do                                                                                                 \
+    {                                                                                                  \
+        if ((s)->multi)                                                                                \
+            return fail(-12, what ": device-pointer entry points need a single-device handle "         \
+                             "(this one shards over %d GPUs)", multi_count(s));                        \
+    } while (0)
 
 /* Back-face culling is applied to an object only when its mesh is PROVEN closed and consistently
  * oriented: after welding vertices with bit-identical positions, every directed edge u->v must occur
@@ -351,6 +382,12 @@ extern "C" const char* dbot_b200_last_error(void) { return g_last_error.c_str();
 extern "C" int dbot_b200_destroy(dbot_b200_sensor* s)
 {
     if (!s) return fail(-1, "destroy: null handle");
+    if (s->multi)
+    {
+        multi_destroy(s);
+        delete s;
+        return 0;
+    }
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_mesh); cudaFree(s->d_chunks); cudaFree(s->d_obs); cudaFree(s->d_tab);
@@ -377,9 +414,10 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     if (e != cudaSuccess || n_dev == 0)
         return fail(e != cudaSuccess ? (int)e : (int)cudaErrorNoDevice,
                     "no CUDA device: libdbot_b200 has no CPU fallback (%s)", cudaGetErrorString(e));
-    if (cfg->device_id < 0 || cfg->device_id >= n_dev)
-        return fail(-2, "device_id %d out of range (have %d)", cfg->device_id, n_dev);
-    s->device = cfg->device_id;
+    const int device_id = (cfg->n_devices == 1 && cfg->device_ids) ? cfg->device_ids[0] : cfg->device_id;
+    if (device_id < 0 || device_id >= n_dev)
+        return fail(-2, "device_id %d out of range (have %d)", device_id, n_dev);
+    s->device = device_id;
     CUDA_TRY(cudaSetDevice(s->device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
@@ -527,7 +565,8 @@ extern "C" int dbot_b200_create(const dbot_b200_config* cfg, dbot_b200_sensor** 
     s->cfg = *cfg;
     s->cfg.vertices = nullptr; s->cfg.triangles = nullptr;
     s->cfg.n_vertices = nullptr; s->cfg.n_triangles = nullptr;
-    int rc = create_impl(cfg, s);
+    if (cfg->n_devices < 0) return fail(-2, "create: n_devices must not be negative");
+    int rc = cfg->n_devices > 1 ? multi_create(cfg, s) : create_impl(cfg, s);
     if (rc)
     {
         std::string keep = g_last_error;
@@ -568,9 +607,20 @@ __global__ void dbot_reset_slots_kernel(int32_t* loc, int32_t* free_stack, int32
     if (i < n_phys - 1) free_stack[i] = n_phys - 1 - i; /* top of the stack = slot 1 */
 }
 
+__global__ void dbot_free_all_slots_kernel(int32_t* free_stack, int32_t* free_count, int n_phys)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *free_count = n_phys;
+    if (i < n_phys) free_stack[i] = n_phys - 1 - i;
+}
+
+static int multi_reset(dbot_b200_sensor* s);
+
 extern "C" int dbot_b200_reset(dbot_b200_sensor* s)
 {
     if (!s) return fail(-1, "reset: null handle");
+    s->poisoned = 0;
+    if (s->multi) return multi_reset(s);
     CUDA_TRY(cudaSetDevice(s->device));
     s->cur = 0;
     s->n_slots = 1;
@@ -618,6 +668,8 @@ static bool is_pinned_host(const void* p)
 extern "C" int dbot_b200_set_observation(dbot_b200_sensor* s, const float* depth_m)
 {
     if (!s || !depth_m) return fail(-1, "set_observation: null argument");
+    DBOT_CHECK_USABLE(s, "set_observation");
+    if (s->multi) return multi_set_observation(s, depth_m);
     CUDA_TRY(cudaSetDevice(s->device));
     const size_t bytes = (size_t)s->kp.rows * s->kp.cols * sizeof(float);
     if (is_pinned_host(depth_m))
@@ -643,6 +695,8 @@ extern "C" int dbot_b200_set_observation(dbot_b200_sensor* s, const float* depth
 extern "C" int dbot_b200_set_observation_device(dbot_b200_sensor* s, const float* d_depth_m)
 {
     if (!s || !d_depth_m) return fail(-1, "set_observation_device: null argument");
+    DBOT_CHECK_USABLE(s, "set_observation_device");
+    DBOT_SINGLE_ONLY(s, "set_observation_device");
     CUDA_TRY(cudaSetDevice(s->device));
     return launch_observation(s, d_depth_m);
 }
@@ -739,18 +793,40 @@ static int launch_particles(dbot_b200_sensor* s, const float* d_poses, int32_t* 
     return 0;
 }
 
-/* RbSensor::loglikes */
-extern "C" int dbot_b200_loglikes(dbot_b200_sensor* s, const float* poses, int32_t* indices,
-                                  int32_t n, int32_t update, double* out_loglikes)
+/* device error flag -> error code; a failed update leaves the handle unusable until reset() */
+static int device_error(dbot_b200_sensor* s, const char* what, int was_update)
 {
-    if (!s || !poses || !indices || !out_loglikes) return fail(-1, "loglikes: null argument");
-    if (n < 0 || n > s->cfg.max_particles)
-        return fail(-2, "loglikes: n=%d exceeds max_particles=%d", n, s->cfg.max_particles);
-    for (int i = 0; i < n; ++i)
-        if (indices[i] < 0 || indices[i] >= s->n_slots)
-            return fail(-7, "loglikes: indices[%d]=%d is not an occlusion slot (have %d)", i,
-                        indices[i], s->n_slots);
-    if (n == 0) return 0;
+    const int code = *s->h_err;
+    if (!code) return 0;
+    cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream);
+    if (was_update) s->poisoned = 1;
+    if (code == 3) return fail(-11, "%s: an adopting particle timed out waiting for its siblings' copies", what);
+    if (code == 2) return fail(-10, "%s: the occlusion-slot pool is exhausted (too many imported slots)", what);
+    return fail(-7, "%s: a parent index was not a valid occlusion slot", what);
+}
+
+/* an update with no particles: every slot is given back, the handle's clock and lazy-propagation state
+ * advance exactly as with particles (a shard that receives no particle of a call must stay in step with
+ * the other shards) */
+static int empty_update(dbot_b200_sensor* s)
+{
+    double A, B;
+    state_affine_now(s, &A, &B);
+    const int n_phys = 2 * s->cfg.max_particles;
+    dbot_free_all_slots_kernel<<<(n_phys + 255) / 256, 256, 0, s->stream>>>(s->d_free, s->d_free_count, n_phys);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    s->n_slots = 0;
+    s->t_update = s->t_obs;
+    s->A = A;
+    s->B = B;
+    return 0;
+}
+
+/* first half of RbSensor::loglikes: stage the host arrays, enqueue copies and kernels, no wait */
+static int loglikes_enqueue(dbot_b200_sensor* s, const float* poses, const int32_t* indices, int32_t n,
+                            int32_t update)
+{
     CUDA_TRY(cudaSetDevice(s->device));
     const size_t pose_bytes = (size_t)n * 12 * s->kp.n_obj * sizeof(float);
     memcpy(s->h_poses, poses, pose_bytes);
@@ -758,21 +834,54 @@ extern "C" int dbot_b200_loglikes(dbot_b200_sensor* s, const float* poses, int32
     CUDA_TRY(cudaMemcpyAsync(s->d_poses, s->h_poses, pose_bytes, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(s->d_indices, s->h_indices, (size_t)n * sizeof(int32_t),
                              cudaMemcpyHostToDevice, s->stream));
-    int rc = launch_particles(s, s->d_poses, s->d_indices, n, update, s->d_out);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(s->h_out, s->d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost,
-                             s->stream));
+    return launch_particles(s, s->d_poses, s->d_indices, n, update, s->d_out);
+}
+/* second half: log-weights and the error flag back, wait, report */
+static int loglikes_finish(dbot_b200_sensor* s, int32_t n, int32_t update, double* out_loglikes)
+{
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (n > 0 && out_loglikes)
+        CUDA_TRY(cudaMemcpyAsync(s->h_out, s->d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaMemcpyAsync(s->h_err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    if (*s->h_err)
-    {
-        const int code = *s->h_err;
-        cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream);
-        if (code == 3) return fail(-11, "loglikes: an adopting particle timed out waiting for its siblings' copies");
-        return code == 2 ? fail(-10, "loglikes: the occlusion-slot pool is exhausted (too many imported slots)")
-                         : fail(-7, "loglikes: a parent index was not a valid occlusion slot");
-    }
-    memcpy(out_loglikes, s->h_out, (size_t)n * sizeof(double));
+    int rc = device_error(s, "loglikes", update);
+    if (rc) return rc;
+    if (n > 0 && out_loglikes) memcpy(out_loglikes, s->h_out, (size_t)n * sizeof(double));
+    return 0;
+}
+
+/* particle-sharded evaluation: the update of a call in which this shard received no particle */
+extern "C" int dbot_b200_update_empty(dbot_b200_sensor* s)
+{
+    if (!s) return fail(-1, "update_empty: null handle");
+    DBOT_CHECK_USABLE(s, "update_empty");
+    DBOT_SINGLE_ONLY(s, "update_empty");
+    CUDA_TRY(cudaSetDevice(s->device));
+    return empty_update(s);
+}
+
+static int multi_loglikes(dbot_b200_sensor* s, const float* poses, int32_t* indices, int32_t n, int32_t update,
+                          double* out_loglikes);
+
+/* RbSensor::loglikes */
+extern "C" int dbot_b200_loglikes(dbot_b200_sensor* s, const float* poses, int32_t* indices,
+                                  int32_t n, int32_t update, double* out_loglikes)
+{
+    if (!s || n < 0) return fail(-1, "loglikes: null handle or negative n");
+    if (n > 0 && (!poses || !indices || !out_loglikes)) return fail(-1, "loglikes: null argument");
+    DBOT_CHECK_USABLE(s, "loglikes");
+    if (n > s->cfg.max_particles)
+        return fail(-2, "loglikes: n=%d exceeds max_particles=%d", n, s->cfg.max_particles);
+    if (s->multi) return multi_loglikes(s, poses, indices, n, update, out_loglikes);
+    for (int i = 0; i < n; ++i)
+        if (indices[i] < 0 || indices[i] >= s->n_slots)
+            return fail(-7, "loglikes: indices[%d]=%d is not an occlusion slot (have %d)", i,
+                        indices[i], s->n_slots);
+    if (n == 0) return 0; /* as dbot's model: a call without particles changes nothing, update or not */
+    int rc = loglikes_enqueue(s, poses, indices, n, update);
+    if (rc) return rc;
+    rc = loglikes_finish(s, n, update, out_loglikes);
+    if (rc) return rc;
     if (update)
         for (int i = 0; i < n; ++i) indices[i] = i;
     return 0;
@@ -785,34 +894,33 @@ extern "C" int dbot_b200_loglikes_device(dbot_b200_sensor* s, const float* d_pos
     if (!s || !d_poses || !d_indices || !d_out_loglikes) return fail(-1, "loglikes_device: null argument");
     if (n < 0 || n > s->cfg.max_particles)
         return fail(-2, "loglikes_device: n=%d exceeds max_particles=%d", n, s->cfg.max_particles);
+    DBOT_CHECK_USABLE(s, "loglikes_device");
+    DBOT_SINGLE_ONLY(s, "loglikes_device");
     if (n == 0) return 0;
     CUDA_TRY(cudaSetDevice(s->device));
+    if (update) s->update_since_sync = 1;
     return launch_particles(s, d_poses, d_indices, n, update, d_out_loglikes);
 }
 
-extern "C" void* dbot_b200_stream(dbot_b200_sensor* s) { return s ? (void*)s->stream : nullptr; }
+extern "C" void* dbot_b200_stream(dbot_b200_sensor* s) { return (s && !s->multi) ? (void*)s->stream : nullptr; }
 
 extern "C" int dbot_b200_synchronize(dbot_b200_sensor* s)
 {
     if (!s) return fail(-1, "synchronize: null handle");
+    DBOT_SINGLE_ONLY(s, "synchronize");
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaMemcpyAsync(s->h_err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    if (*s->h_err)
-    {
-        const int code = *s->h_err;
-        cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream);
-        if (code == 2) return fail(-10, "the occlusion-slot pool is exhausted (too many imported slots)");
-        if (code == 3) return fail(-11, "an adopting particle timed out waiting for its siblings' copies");
-        return fail(-7, "loglikes_device: an index was not a valid occlusion slot");
-    }
-    return 0;
+    const int was_update = s->update_since_sync;
+    s->update_since_sync = 0;
+    return device_error(s, "loglikes_device", was_update);
 }
 
 /* RigidBodyRenderer::Render for one pose set */
 extern "C" int dbot_b200_render(dbot_b200_sensor* s, const float* pose, float* out_depth)
 {
     if (!s || !pose || !out_depth) return fail(-1, "render: null argument");
+    if (s->multi) s = multi_child(s, 0);
     CUDA_TRY(cudaSetDevice(s->device));
     const size_t P = (size_t)s->kp.rows * s->kp.cols;
     const size_t pose_bytes = (size_t)12 * s->kp.n_obj * sizeof(float);
@@ -847,12 +955,15 @@ extern "C" int dbot_b200_render(dbot_b200_sensor* s, const float* pose, float* o
 }
 
 /* ---- state read-back ---- */
-extern "C" int dbot_b200_n_slots(dbot_b200_sensor* s) { return s ? s->n_slots : -1; }
+extern "C" int dbot_b200_n_slots(dbot_b200_sensor* s) { return !s ? -1 : (s->multi ? multi_n_slots(s) : s->n_slots); }
 extern "C" int dbot_b200_cull_sign(dbot_b200_sensor* s, int32_t object)
 {
     return (s && object >= 0 && object < s->cfg.n_objects) ? s->cull_signs[object] : 0;
 }
-extern "C" double dbot_b200_observation_time(dbot_b200_sensor* s) { return s ? s->t_obs : NAN; }
+extern "C" double dbot_b200_observation_time(dbot_b200_sensor* s)
+{
+    return !s ? NAN : (s->multi ? multi_child(s, 0)->t_obs : s->t_obs);
+}
 
 /* ---- occlusion-slot migration between handles (cross-GPU resampling) ---- */
 __global__ void dbot_export_slot_kernel(const float* __restrict__ pool, const int32_t* __restrict__ loc,
@@ -892,6 +1003,7 @@ extern "C" int64_t dbot_b200_slot_floats(dbot_b200_sensor* s) { return s ? (int6
 extern "C" int dbot_b200_export_slot_device(dbot_b200_sensor* s, int32_t slot, float* d_dst)
 {
     if (!s || !d_dst) return fail(-1, "export_slot: null argument");
+    DBOT_SINGLE_ONLY(s, "export_slot");
     if (slot < 0 || slot >= s->n_slots) return fail(-7, "export_slot: slot %d of %d", slot, s->n_slots);
     CUDA_TRY(cudaSetDevice(s->device));
     dbot_export_slot_kernel<<<64, 256, 0, s->stream>>>(s->d_pool, s->d_loc[s->cur], slot, s->kp.slot_stride, d_dst);
@@ -903,6 +1015,7 @@ extern "C" int dbot_b200_export_slot_device(dbot_b200_sensor* s, int32_t slot, f
 extern "C" int dbot_b200_import_slot_device(dbot_b200_sensor* s, const float* d_src, int32_t* out_slot)
 {
     if (!s || !d_src || !out_slot) return fail(-1, "import_slot: null argument");
+    DBOT_SINGLE_ONLY(s, "import_slot");
     /* live + imported slots stay within half of the pool, so that an update can always find a fresh
      * slot for every copying child (every imported slot is some child's parent and is adopted) */
     if (s->n_slots >= 2 * s->cfg.max_particles - 1)
@@ -921,6 +1034,17 @@ extern "C" int dbot_b200_import_slot_device(dbot_b200_sensor* s, const float* d_
 extern "C" int dbot_b200_free_slot_count(dbot_b200_sensor* s)
 {
     if (!s) return -1;
+    if (s->multi)
+    {
+        int total = 0;
+        for (int g = 0; g < multi_count(s); ++g)
+        {
+            const int f = dbot_b200_free_slot_count(multi_child(s, g));
+            if (f < 0) return -1;
+            total += f;
+        }
+        return total;
+    }
     if (cudaSetDevice(s->device) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess) return -1;
     int32_t f = -1;
     if (cudaMemcpy(&f, s->d_free_count, sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
@@ -930,6 +1054,13 @@ extern "C" int dbot_b200_free_slot_count(dbot_b200_sensor* s)
 extern "C" int dbot_b200_get_occlusion(dbot_b200_sensor* s, int32_t slot, float* out_occ)
 {
     if (!s || !out_occ) return fail(-1, "get_occlusion: null argument");
+    if (s->multi)
+    {
+        if (slot < 0 || slot >= multi_n_slots(s)) return fail(-7, "get_occlusion: slot %d of %d", slot, multi_n_slots(s));
+        int32_t local = 0;
+        dbot_b200_sensor* owner = multi_owner(s, slot, &local);
+        return dbot_b200_get_occlusion(owner, local, out_occ);
+    }
     if (slot < 0 || slot >= s->n_slots) return fail(-7, "get_occlusion: slot %d of %d", slot, s->n_slots);
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -951,6 +1082,7 @@ extern "C" int dbot_b200_get_occlusion(dbot_b200_sensor* s, int32_t slot, float*
 extern "C" int dbot_b200_timer_begin(dbot_b200_sensor* s)
 {
     if (!s) return fail(-1, "timer_begin: null handle");
+    if (s->multi) return multi_timer_begin(s);
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaEventRecord(s->ev_begin, s->stream));
     return 0;
@@ -958,6 +1090,7 @@ extern "C" int dbot_b200_timer_begin(dbot_b200_sensor* s)
 extern "C" int dbot_b200_timer_end(dbot_b200_sensor* s, float* out_ms)
 {
     if (!s || !out_ms) return fail(-1, "timer_end: null argument");
+    if (s->multi) return multi_timer_end(s, out_ms);
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaEventRecord(s->ev_end, s->stream));
     CUDA_TRY(cudaEventSynchronize(s->ev_end));
@@ -967,6 +1100,11 @@ extern "C" int dbot_b200_timer_end(dbot_b200_sensor* s, float* out_ms)
 extern "C" int dbot_b200_profile_enable(dbot_b200_sensor* s, int32_t on)
 {
     if (!s) return fail(-1, "profile_enable: null handle");
+    if (s->multi)
+    {
+        for (int g = 0; g < multi_count(s); ++g) dbot_b200_profile_enable(multi_child(s, g), on);
+        return 0;
+    }
     s->profile = on ? 1 : 0;
     memset(s->prof_ms, 0, sizeof(s->prof_ms));
     memset(s->prof_launches, 0, sizeof(s->prof_launches));
@@ -975,13 +1113,47 @@ extern "C" int dbot_b200_profile_enable(dbot_b200_sensor* s, int32_t on)
 extern "C" int dbot_b200_profile_read(dbot_b200_sensor* s, float* out_ms, int64_t* out_launches)
 {
     if (!s || !out_ms || !out_launches) return fail(-1, "profile_read: null argument");
+    if (s->multi) /* the slowest shard's time per kernel kind, launches summed over the shards */
+    {
+        float ms[DBOT_B200_KERNEL_COUNT];
+        int64_t cnt[DBOT_B200_KERNEL_COUNT];
+        for (int k = 0; k < DBOT_B200_KERNEL_COUNT; ++k) { out_ms[k] = 0.f; out_launches[k] = 0; }
+        for (int g = 0; g < multi_count(s); ++g)
+        {
+            dbot_b200_profile_read(multi_child(s, g), ms, cnt);
+            for (int k = 0; k < DBOT_B200_KERNEL_COUNT; ++k)
+            {
+                out_ms[k] = std::max(out_ms[k], ms[k]);
+                out_launches[k] += cnt[k];
+            }
+        }
+        return 0;
+    }
     memcpy(out_ms, s->prof_ms, sizeof(s->prof_ms));
     memcpy(out_launches, s->prof_launches, sizeof(s->prof_launches));
     memset(s->prof_ms, 0, sizeof(s->prof_ms));
     memset(s->prof_launches, 0, sizeof(s->prof_launches));
     return 0;
 }
-extern "C" int64_t dbot_b200_launch_count(dbot_b200_sensor* s) { return s ? s->launches : -1; }
-extern "C" int64_t dbot_b200_device_bytes(dbot_b200_sensor* s) { return s ? s->device_bytes : -1; }
+extern "C" int64_t dbot_b200_launch_count(dbot_b200_sensor* s)
+{
+    if (!s) return -1;
+    if (!s->multi) return s->launches;
+    int64_t t = 0;
+    for (int g = 0; g < multi_count(s); ++g) t += multi_child(s, g)->launches;
+    return t;
+}
+extern "C" int64_t dbot_b200_device_bytes(dbot_b200_sensor* s)
+{
+    if (!s) return -1;
+    if (!s->multi) return s->device_bytes;
+    int64_t t = 0;
+    for (int g = 0; g < multi_count(s); ++g) t += multi_child(s, g)->device_bytes;
+    return t;
+}
 
 #include "dbot_filter.cuh"
+#include "multi_device.cuh"
+static int multi_n_slots(dbot_b200_sensor* s) { return s->multi->n_slots; }
+static dbot_b200_sensor* multi_child(dbot_b200_sensor* s, int g) { return s->multi->child[g]; }
+static int multi_count(dbot_b200_sensor* s) { return s->multi->G; }

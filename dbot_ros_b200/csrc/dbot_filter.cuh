@@ -38,12 +38,43 @@ struct dbot_b200_filter
     float* d_poses;        /* [n][n_obj][12] */
     int32_t* d_parents;    /* [n] */
     double* d_cdf;         /* [n] */
-    double* d_integrated;  /* [n_obj][6] + [n_obj][9] rotation matrices */
+    double* d_integrated;  /* [n_obj][6] poses + [n_obj][9] rotation matrices + [n_obj][6] mean velocities */
     int32_t* d_info;       /* [0] resamplings since initialize, [1] resample flag of the current block */
-    double* h_integrated;  /* pinned [n_obj][6] */
+    double* h_integrated;  /* pinned, same layout */
     int32_t* h_info;       /* pinned [2] */
     int cur;
+    /* Tracker::track's moving average over the published state (centre frame), host side */
+    double smoothed[DBOT_B200_MAX_OBJECTS][12];
+    int have_smoothed;
 };
+
+/* ---- host: rotation vector <-> quaternion, for the moving average and the centre <-> model frame ---- */
+static void dbot_h_quat(const double* v, double* q)
+{
+    const double a = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    const double k = a > 1e-12 ? sin(0.5 * a) / a : 0.5;
+    q[0] = cos(0.5 * a); q[1] = k * v[0]; q[2] = k * v[1]; q[3] = k * v[2];
+}
+static void dbot_h_rotvec(const double* q, double* v)
+{
+    double w = q[0], x = q[1], y = q[2], z = q[3];
+    if (w < 0.0) { w = -w; x = -x; y = -y; z = -z; }
+    const double sn = sqrt(x * x + y * y + z * z);
+    const double a = 2.0 * atan2(sn, w);
+    const double k = sn > 1e-12 ? a / sn : 2.0;
+    v[0] = k * x; v[1] = k * y; v[2] = k * z;
+}
+/* R(v) c, Rodrigues */
+static void dbot_h_rotate(const double* v, const double* c, double* out)
+{
+    const double a = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (!(a > 0.0)) { out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; return; }
+    const double k[3] = {v[0] / a, v[1] / a, v[2] / a};
+    const double cs = cos(a), sn = sin(a);
+    const double kc = k[0] * c[0] + k[1] * c[1] + k[2] * c[2];
+    const double kxc[3] = {k[1] * c[2] - k[2] * c[1], k[2] * c[0] - k[0] * c[2], k[0] * c[1] - k[1] * c[0]};
+    for (int i = 0; i < 3; ++i) out[i] = c[i] * cs + kxc[i] * sn + k[i] * kc * (1.0 - cs);
+}
 
 /* ---- counter-based noise: splitmix64 of (seed, frame, block, particle, pair) -> Box-Muller ---- */
 __host__ __device__ inline uint64_t dbot_splitmix64(uint64_t x)
@@ -284,12 +315,12 @@ __global__ void __launch_bounds__(DBOT_FILTER_THREADS, 1)
                             const double* __restrict__ log_w, double* __restrict__ integrated, int n, int n_obj)
 {
     __shared__ double s_red[DBOT_FILTER_THREADS / 32];
-    __shared__ double s_mean[6];
+    __shared__ double s_mean[12];
     __shared__ double s_Rm[9];
     const int t = threadIdx.x;
     for (int o = 0; o < n_obj; ++o)
     {
-        for (int d = 0; d < 6; ++d)
+        for (int d = 0; d < 12; ++d) /* pose delta and velocity (the State the reference publishes carries both) */
         {
             double acc = 0.0;
             for (int i = t; i < n; i += DBOT_FILTER_THREADS) acc += exp(log_w[i]) * next[((size_t)i * n_obj + o) * 12 + d];
@@ -309,6 +340,7 @@ __global__ void __launch_bounds__(DBOT_FILTER_THREADS, 1)
                 integrated[6 * o + k] += s_mean[k];
                 integrated[6 * o + 3 + k] = v[k];
             }
+            for (int k = 0; k < 6; ++k) integrated[15 * n_obj + 6 * o + k] = s_mean[6 + k];
         }
         __syncthreads();
         for (int i = t; i < n; i += DBOT_FILTER_THREADS)
@@ -363,12 +395,15 @@ extern "C" int dbot_b200_filter_create(dbot_b200_sensor* s, const dbot_b200_filt
 {
     if (!s || !cfg || !out) return fail(-1, "filter_create: null argument");
     *out = nullptr;
+    DBOT_SINGLE_ONLY(s, "filter_create");
     const int n_obj = s->kp.n_obj;
     const int n = cfg->n_particles;
     if (n <= 0 || n > s->cfg.max_particles)
         return fail(-2, "filter_create: n_particles=%d not in [1,%d]", n, s->cfg.max_particles);
     if (!(cfg->velocity_factor >= 0.0) || !(cfg->max_kl_divergence >= 0.0))
         return fail(-4, "filter_create: velocity_factor and max_kl_divergence must be non-negative");
+    if (!(cfg->moving_average_update_rate > 0.0) || cfg->moving_average_update_rate > 1.0)
+        return fail(-4, "filter_create: moving_average_update_rate must be in (0, 1]");
     CUDA_TRY(cudaSetDevice(s->device));
     dbot_b200_filter* f = new dbot_b200_filter();
     memset(f, 0, sizeof(*f));
@@ -392,9 +427,9 @@ extern "C" int dbot_b200_filter_create(dbot_b200_sensor* s, const dbot_b200_filt
     alloc((void**)&f->d_poses, (size_t)n * n_obj * 12 * sizeof(float));
     alloc((void**)&f->d_parents, n * sizeof(int32_t));
     alloc((void**)&f->d_cdf, n * sizeof(double));
-    alloc((void**)&f->d_integrated, (size_t)n_obj * 15 * sizeof(double));
+    alloc((void**)&f->d_integrated, (size_t)n_obj * 21 * sizeof(double));
     alloc((void**)&f->d_info, 2 * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&f->h_integrated, (size_t)n_obj * 6 * sizeof(double), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&f->h_integrated, (size_t)n_obj * 21 * sizeof(double), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&f->h_info, 2 * sizeof(int32_t), cudaHostAllocDefault);
     if (e != cudaSuccess)
     {
@@ -413,6 +448,16 @@ extern "C" int dbot_b200_filter_initialize(dbot_b200_filter* f, const double* po
     int rc = dbot_b200_reset(s);
     if (rc) return rc;
     memcpy(f->h_integrated, poses, (size_t)f->n_obj * 6 * sizeof(double));
+    /* dbot Tracker::initialize -> to_center_coordinate_system: the filter tracks the centred mesh, whose
+     * origin sits at R c in the model frame the caller speaks (center_object_frame,
+     * ref:source/dbot_ros/tracker/particle_tracker_node.cpp:210-214) */
+    for (int o = 0; o < f->n_obj; ++o)
+    {
+        double rc[3];
+        dbot_h_rotate(poses + 6 * o + 3, f->cfg.centers[o], rc);
+        for (int k = 0; k < 3; ++k) f->h_integrated[6 * o + k] += rc[k];
+    }
+    f->have_smoothed = 0;
     /* staged through d_cdf-independent scratch: the tail of d_integrated is rewritten by the kernel */
     double* d_tmp = nullptr;
     CUDA_TRY(cudaMalloc(&d_tmp, (size_t)f->n_obj * 6 * sizeof(double)));
@@ -434,12 +479,13 @@ extern "C" int dbot_b200_filter_initialize(dbot_b200_filter* f, const double* po
     return 0;
 }
 
-/* Tracker::track (ref:source/dbot_ros/object_tracker_ros.hpp:49): one depth frame in, the new
- * integrated poses [n_obj][6] out; out_resamplings = resampling steps since initialize */
-extern "C" int dbot_b200_filter_track(dbot_b200_filter* f, const float* depth_m, double* out_poses,
+/* Tracker::track (ref:source/dbot_ros/object_tracker_ros.hpp:49-61): one depth frame in, the published state
+ * [n_obj][12] out (position, rotation vector, linear and angular velocity; model frame, moving average
+ * applied); out_resamplings = resampling steps since initialize */
+extern "C" int dbot_b200_filter_track(dbot_b200_filter* f, const float* depth_m, double* out_states,
                                       int32_t* out_resamplings)
 {
-    if (!f || !depth_m || !out_poses) return fail(-1, "filter_track: null argument");
+    if (!f || !depth_m || !out_states) return fail(-1, "filter_track: null argument");
     dbot_b200_sensor* s = f->s;
     CUDA_TRY(cudaSetDevice(s->device));
     int rc = dbot_b200_set_observation(s, depth_m);
@@ -472,17 +518,48 @@ extern "C" int dbot_b200_filter_track(dbot_b200_filter* f, const float* depth_m,
                                                                       f->d_integrated, n, n_obj);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(f->h_integrated, f->d_integrated, (size_t)n_obj * 6 * sizeof(double),
+    CUDA_TRY(cudaMemcpyAsync(f->h_integrated, f->d_integrated, (size_t)n_obj * 21 * sizeof(double),
                              cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaMemcpyAsync(f->h_info, f->d_info, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaMemcpyAsync(s->h_err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    if (*s->h_err)
+    rc = device_error(s, "filter_track", 1);
+    if (rc) return rc;
+    /* dbot Tracker::track: moving average over the state (positions and velocities linearly, orientations as
+     * quaternions), then back to the model frame (to_model_coordinate_system) */
+    const double a = f->cfg.moving_average_update_rate;
+    for (int o = 0; o < n_obj; ++o)
     {
-        cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream);
-        return fail(-7, "filter_track: the sensor rejected a parent slot");
+        double cur[12];
+        for (int k = 0; k < 6; ++k) cur[k] = f->h_integrated[6 * o + k];
+        for (int k = 0; k < 6; ++k) cur[6 + k] = f->h_integrated[15 * n_obj + 6 * o + k];
+        double* sm = f->smoothed[o];
+        if (!f->have_smoothed || a >= 1.0)
+            memcpy(sm, cur, sizeof(cur));
+        else
+        {
+            double qa[4], qb[4];
+            dbot_h_quat(sm + 3, qa);
+            dbot_h_quat(cur + 3, qb);
+            const double sgn = (qa[0] * qb[0] + qa[1] * qb[1] + qa[2] * qb[2] + qa[3] * qb[3]) < 0.0 ? -1.0 : 1.0;
+            double nrm = 0.0;
+            for (int k = 0; k < 4; ++k)
+            {
+                qa[k] = (1.0 - a) * qa[k] + a * sgn * qb[k];
+                nrm += qa[k] * qa[k];
+            }
+            nrm = sqrt(nrm);
+            for (int k = 0; k < 4; ++k) qa[k] /= nrm;
+            for (int k = 0; k < 3; ++k) sm[k] = (1.0 - a) * sm[k] + a * cur[k];
+            dbot_h_rotvec(qa, sm + 3);
+            for (int k = 6; k < 12; ++k) sm[k] = (1.0 - a) * sm[k] + a * cur[k];
+        }
+        double rc3[3];
+        dbot_h_rotate(sm + 3, f->cfg.centers[o], rc3);
+        for (int k = 0; k < 12; ++k) out_states[12 * o + k] = sm[k];
+        for (int k = 0; k < 3; ++k) out_states[12 * o + k] -= rc3[k];
     }
-    memcpy(out_poses, f->h_integrated, (size_t)n_obj * 6 * sizeof(double));
+    f->have_smoothed = 1;
     if (out_resamplings) *out_resamplings = f->h_info[0];
     f->frame += 1;
     return 0;

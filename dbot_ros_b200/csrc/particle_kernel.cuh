@@ -441,6 +441,8 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
             if (tid == 0)
             {
                 p.out[i] = __longlong_as_double(0x7ff8000000000000LL);
+                for (int g = 0; g < p.n_peers; ++g)
+                    p.peer_out[g][p.out_offset + i] = __longlong_as_double(0x7ff8000000000000LL);
                 atomicExch(p.err_flag, 1);
             }
             continue;
@@ -563,7 +565,6 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
             {
                 const int rb1 = min(rb0 + tile_rows - 1, r1);
                 const int c0 = cb0, c1 = min(cb0 + tile_cols - 1, wc1), ww = c1 - c0 + 1; /* this tile */
-                const int npx = (rb1 - rb0 + 1) * ww;
                 if (!MULTI)
                 {
                     stage_chunk(0); /* resident after the first particle */
@@ -684,6 +685,9 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
 #pragma unroll
                 for (int w = 0; w < DBOT_CW; ++w) s += s_red[w];
                 p.out[i] = s;
+                /* fused gather (multi_device.cuh, gather_mode 1): the log-weight goes straight into every
+                 * GPU's gathered vector over NVLink peer memory */
+                for (int g = 0; g < p.n_peers; ++g) p.peer_out[g][p.out_offset + i] = s;
 #ifdef DBOT_DBG_TIMELINE
                 DBOT_TL();
                 if (blockIdx.x == 3 && k >= 3 * (int)gridDim.x && k < 5 * (int)gridDim.x)

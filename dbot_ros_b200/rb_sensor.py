@@ -214,7 +214,7 @@ class B200KinectImageModel(RbSensor):
     KinectImageModelGPU stood, backed by libdbot_b200.so."""
 
     def __init__(self, camera_matrix, rows, cols, max_sample_count, object_model, params,
-                 device_id=0, occlusion_mode=0):
+                 device_id=0, occlusion_mode=0, device_ids=None, gather_mode=0):
         self._lib = abi.load_library()
         self._h = C.c_void_p()
         self.rows, self.cols = int(rows), int(cols)
@@ -230,7 +230,8 @@ class B200KinectImageModel(RbSensor):
             p_occluded_occluded=params.occlusion.p_occluded_occluded,
             initial_occlusion_prob=params.occlusion.initial_occlusion_prob,
             delta_time=params.delta_time, device_id=device_id, occlusion_mode=occlusion_mode,
-            cull_backfaces=0 if getattr(params, "cull_backfaces", True) else 1)
+            cull_backfaces=0 if getattr(params, "cull_backfaces", True) else 1,
+            device_ids=device_ids, gather_mode=gather_mode)
         abi.check(self._lib, self._lib.dbot_b200_create(C.byref(cfg), C.byref(self._h)))
         # RbSensor::default_poses_ -- one PoseVector (position, euler vector) per object
         self._default_poses = np.zeros((self.n_objects, 6))
@@ -316,6 +317,18 @@ class B200KinectImageModel(RbSensor):
     def n_slots(self):
         return self._lib.dbot_b200_n_slots(self._h)
 
+    @property
+    def device_count(self):
+        """GPUs behind this sensor (particles are sharded over them inside the library)"""
+        return self._lib.dbot_b200_device_count(self._h)
+
+    @property
+    def migrated_slots(self):
+        return int(self._lib.dbot_b200_migrated_slots(self._h))
+
+    def update_empty(self):
+        abi.check(self._lib, self._lib.dbot_b200_update_empty(self._h))
+
     def cull_sign(self, obj):
         """+1 / -1: back faces of this object are skipped (mesh proven closed); 0: all triangles drawn"""
         return self._lib.dbot_b200_cull_sign(self._h, int(obj))
@@ -378,11 +391,15 @@ class RbSensorBuilder:
 
     Parameters = Parameters
 
-    def __init__(self, object_model, camera_data, params, device_id=0):
+    def __init__(self, object_model, camera_data, params, device_id=0, device_ids=None, gather_mode=0):
+        """device_ids: several CUDA ordinals -> one sensor whose particles are sharded over those GPUs inside
+        the library (one process, BASELINE config 4); gather_mode 0 = ncclAllGather, 1 = fused peer stores"""
         self.object_model = object_model
         self.camera_data = camera_data
         self.params = params
         self.device_id = device_id
+        self.device_ids = device_ids
+        self.gather_mode = gather_mode
 
     def build(self):
         if not self.params.use_gpu:
@@ -391,4 +408,5 @@ class RbSensorBuilder:
                 "(the CPU model stays dbot's KinectImageModel)")
         return B200KinectImageModel(
             self.camera_data.camera_matrix, self.camera_data.rows, self.camera_data.cols,
-            self.params.sample_count, self.object_model, self.params, device_id=self.device_id)
+            self.params.sample_count, self.object_model, self.params, device_id=self.device_id,
+            device_ids=self.device_ids, gather_mode=self.gather_mode)

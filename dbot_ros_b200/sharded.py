@@ -88,6 +88,23 @@ class ShardedRbSensor(RbSensor):
     def loglikes(self, deltas, indices, update=False):
         return self.loglikes_poses(self.local.compose(deltas), indices, update)
 
+    # RbSensor::integrated_poses / default poses live in the local sensor (it composes the deltas):
+    # a tracker that assigns them on the sharded sensor must reach that one
+    @property
+    def integrated_poses(self):
+        return self.local.integrated_poses
+
+    @integrated_poses.setter
+    def integrated_poses(self, poses):
+        self.local.integrated_poses = poses
+
+    @property
+    def n_objects(self):
+        return self.local.n_objects
+
+    def compose(self, deltas):
+        return self.local.compose(deltas)
+
     # -- pieces ------------------------------------------------------------------------------
     def _forget_imports(self):
         self._imported_keys = [set() for _ in range(self.world)]
@@ -226,6 +243,43 @@ class ShardedRbSensor(RbSensor):
             got = self._buf.numpy().reshape(self.world, width)
         return np.concatenate([got[r, : counts[r]] for r in range(self.world)])
 
+    def _evaluate_and_gather_on_device(self, poses, lo, hi, local_idx, n, update):
+        """CUDA path: this rank's slice goes to the device once, the kernel's output is all-gathered where it
+        lies (NCCL over NVLink), the gathered vector comes back with one copy -- one stream, one wait per call"""
+        import torch
+        import torch.distributed as dist
+
+        counts = shard_counts(n, self.world)
+        width = max(counts)
+        cnt = hi - lo
+        n_obj = self.local.n_objects
+        if self._buf is None or self._buf.numel() < width * self.world:
+            cap = max(width, getattr(self.local, "max_sample_count", width))
+            self._h_poses = torch.zeros((cap, n_obj, 12), dtype=torch.float32).pin_memory()
+            self._h_idx = torch.zeros(cap, dtype=torch.int32).pin_memory()
+            self._d_poses = torch.zeros((cap, n_obj, 12), dtype=torch.float32, device=self.device)
+            self._d_idx = torch.zeros(cap, dtype=torch.int32, device=self.device)
+            self._d_out = torch.zeros(cap, dtype=torch.float64, device=self.device)
+            self._buf = torch.zeros(cap * self.world, dtype=torch.float64, device=self.device)
+            self._h_all = torch.zeros(cap * self.world, dtype=torch.float64).pin_memory()
+            self._ext = torch.cuda.ExternalStream(self.local.stream, device=self.device)
+        if cnt:
+            self._h_poses[:cnt] = torch.from_numpy(poses[lo:hi])
+            self._h_idx[:cnt] = torch.from_numpy(local_idx)
+        with torch.cuda.stream(self._ext):
+            if cnt:
+                self._d_poses[:cnt].copy_(self._h_poses[:cnt], non_blocking=True)
+                self._d_idx[:cnt].copy_(self._h_idx[:cnt], non_blocking=True)
+                self.local.loglikes_device(self._d_poses.data_ptr(), self._d_idx.data_ptr(), cnt, update,
+                                           self._d_out.data_ptr())
+            elif update:
+                self.local.update_empty()
+            dist.all_gather_into_tensor(self._buf[: width * self.world], self._d_out[:width], group=self.group)
+            self._h_all[: width * self.world].copy_(self._buf[: width * self.world], non_blocking=True)
+        self.local.synchronize()   # the one wait of the call; also surfaces device-side errors
+        got = self._h_all[: width * self.world].numpy().reshape(self.world, width)
+        return np.concatenate([got[r, : counts[r]] for r in range(self.world)])
+
     def loglikes_poses(self, poses, indices, update=False):
         n_obj = self.local.n_objects
         poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, n_obj, 12)
@@ -236,8 +290,16 @@ class ShardedRbSensor(RbSensor):
             raise IndexError("loglikes: parent slot out of range (have %d)" % self.n_slots)
         self.migrate(indices, n)
         lo, hi, local_idx = self.local_parents(indices, n)
-        mine = self.local.loglikes_poses(poses[lo:hi], local_idx, update) if hi > lo else np.zeros(0)
-        out = self.all_gather(mine, n)
+        if self.device.type == "cuda" and hasattr(self.local, "loglikes_device"):
+            out = self._evaluate_and_gather_on_device(poses, lo, hi, local_idx, n, update)
+        else:
+            if hi > lo:
+                mine = self.local.loglikes_poses(poses[lo:hi], local_idx, update)
+            else:
+                mine = np.zeros(0)
+                if update and hasattr(self.local, "update_empty"):
+                    self.local.update_empty()   # stay in step with the shards that did get particles
+            out = self.all_gather(mine, n)
         if update:
             indices[:] = np.arange(n, dtype=np.int32)
             self.n_slots = n

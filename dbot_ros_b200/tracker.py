@@ -45,6 +45,67 @@ class TrackerParameters:
     max_kl_divergence: float = 2.0
     delta_time: float = 1.0 / 30.0
     transition: ObjectTransitionParameters = field(default_factory=ObjectTransitionParameters)
+    center_object_frame: bool = False   # ref:config/particle_tracker.yaml:30, ref:...particle_tracker_node.cpp:212-214
+
+
+# ---- Tracker::track post-processing shared by both trackers (dbot tracker/tracker.cpp, un-vendored) ----------
+def _quat(v):
+    a = float(np.linalg.norm(v))
+    k = np.sin(0.5 * a) / a if a > 1e-12 else 0.5
+    return np.concatenate([[np.cos(0.5 * a)], k * np.asarray(v, dtype=np.float64)])
+
+
+def _rotvec_of_quat(q):
+    q = -q if q[0] < 0.0 else q
+    sn = float(np.linalg.norm(q[1:]))
+    a = 2.0 * np.arctan2(sn, q[0])
+    return (a / sn if sn > 1e-12 else 2.0) * q[1:]
+
+
+def moving_average(smoothed, current, rate):
+    """states [n_obj][12]: positions and velocities blend linearly, orientations as quaternions (sign-aligned,
+    renormalised) -- dbot's Tracker keeps a moving average of the state it returns
+    (moving_average_update_rate, ref:config/particle_tracker.yaml:25)"""
+    if smoothed is None or rate >= 1.0:
+        return current.copy()
+    out = (1.0 - rate) * smoothed + rate * current
+    for o in range(current.shape[0]):
+        qa, qb = _quat(smoothed[o, 3:6]), _quat(current[o, 3:6])
+        if np.dot(qa, qb) < 0.0:
+            qb = -qb
+        q = (1.0 - rate) * qa + rate * qb
+        out[o, 3:6] = _rotvec_of_quat(q / np.linalg.norm(q))
+    return out
+
+
+def to_center_frame(poses, centers):
+    """model frame -> frame of the centred mesh (dbot Tracker::to_center_coordinate_system): t += R c"""
+    from .rb_sensor import rotation_matrices
+
+    out = np.array(poses, dtype=np.float64, copy=True)
+    for o, c in enumerate(centers):
+        out[o, 0:3] += rotation_matrices(out[o, 3:6]) @ np.asarray(c, dtype=np.float64)
+    return out
+
+
+def to_model_frame(states, centers):
+    """inverse of to_center_frame (dbot Tracker::to_model_coordinate_system): t -= R c"""
+    from .rb_sensor import rotation_matrices
+
+    out = np.array(states, dtype=np.float64, copy=True)
+    for o, c in enumerate(centers):
+        out[o, 0:3] -= rotation_matrices(out[o, 3:6]) @ np.asarray(c, dtype=np.float64)
+    return out
+
+
+def _centers_for(params, n_obj, centers):
+    if centers is None:
+        if params.center_object_frame:
+            raise ValueError("center_object_frame is set: pass the ObjectModel's centers (object_model.centers) "
+                             "so that poses can be converted between the model frame and the centred mesh")
+        return np.zeros((n_obj, 3))
+    c = np.asarray(centers, dtype=np.float64).reshape(n_obj, 3)
+    return c if params.center_object_frame else np.zeros((n_obj, 3))
 
 
 # ---- counter-based noise shared with the device-resident filter (csrc/dbot_filter.cuh) ----------
@@ -100,11 +161,14 @@ class ParticleTracker:
     ref:source/dbot_ros/object_tracker_ros.hpp:49).  States are deltas relative to the sensor's
     integrated poses: [n][n_obj][12] = position, rotation vector, linear velocity, angular velocity."""
 
-    def __init__(self, sensor, n_objects, params: TrackerParameters, seed=0, counter_noise=False):
+    def __init__(self, sensor, n_objects, params: TrackerParameters, seed=0, counter_noise=False, centers=None):
         """counter_noise: draw the noise from the counter-based generator of the device-resident
-        filter (same seed -> same noise on both) instead of numpy's generator"""
+        filter (same seed -> same noise on both) instead of numpy's generator.
+        centers: ObjectModel.centers when the meshes were centred (center_object_frame): initialize() and
+        track() speak the MODEL frame, as the reference's tracker does."""
         self.sensor = sensor
         self.n_obj = int(n_objects)
+        self.centers = _centers_for(params, self.n_obj, centers)
         self.p = params
         self.seed = int(seed)
         self.counter_noise = counter_noise
@@ -120,8 +184,10 @@ class ParticleTracker:
 
     # -- Tracker::initialize ------------------------------------------------------------------
     def initialize(self, initial_poses):
-        """initial_poses: [n_obj][6] position + rotation vector in the camera frame"""
-        self.sensor.integrated_poses = np.asarray(initial_poses, dtype=np.float64).reshape(self.n_obj, 6)
+        """initial_poses: [n_obj][6] position + rotation vector of the model frame in the camera frame"""
+        poses = np.asarray(initial_poses, dtype=np.float64).reshape(self.n_obj, 6)
+        self.sensor.integrated_poses = to_center_frame(poses, self.centers)
+        self.smoothed = None
         self.states[:] = 0.0
         self.log_w[:] = -np.log(self.n)
         self.indices[:] = 0
@@ -179,9 +245,12 @@ class ParticleTracker:
     def track(self, image):
         from .rb_sensor import rotation_matrices
 
+        """-> [n_obj][12]: position, rotation vector, linear and angular velocity (the State the reference
+        publishes, ref:source/dbot_ros/object_tracker_ros.hpp:49-61), moving average applied, model frame"""
         self.filter(image)
         w = np.exp(self.log_w)
         mean = np.tensordot(w, self.states[:, :, 0:6], axes=(0, 0))            # [n_obj][6]
+        mean_vel = np.tensordot(w, self.states[:, :, 6:12], axes=(0, 0))
         # fold the mean delta into the integrated pose and re-base the particles on it
         poses = self.sensor.integrated_poses
         for o in range(self.n_obj):
@@ -193,9 +262,8 @@ class ParticleTracker:
             Rd = rotation_matrices(self.states[:, o, 3:6])
             self.states[:, o, 3:6] = rotation_vectors(Rd @ Rm.T)
         self.sensor.integrated_poses = poses
-        a = self.p.moving_average_update_rate
-        self.smoothed = poses.copy() if self.smoothed is None or a >= 1.0 else (1 - a) * self.smoothed + a * poses
-        return self.smoothed.copy()
+        self.smoothed = moving_average(self.smoothed, np.hstack([poses, mean_vel]), self.p.moving_average_update_rate)
+        return to_model_frame(self.smoothed, self.centers)
 
 
 def rotation_vector(R):
@@ -218,7 +286,7 @@ class DeviceParticleTracker:
     per frame the depth image goes in and the integrated poses come out; particles, poses, parent
     indices and weights never leave HBM."""
 
-    def __init__(self, sensor, params: TrackerParameters, seed=0):
+    def __init__(self, sensor, params: TrackerParameters, seed=0, centers=None):
         import ctypes as C
 
         from . import abi
@@ -226,6 +294,7 @@ class DeviceParticleTracker:
         self._C, self._abi = C, abi
         self.sensor = sensor
         self.n_obj = sensor.n_objects
+        self.centers = _centers_for(params, self.n_obj, centers)
         self.n = max(1, params.evaluation_count // self.n_obj)
         cfg = abi.FilterConfig()
         for k in range(3):
@@ -235,6 +304,10 @@ class DeviceParticleTracker:
         cfg.max_kl_divergence = params.max_kl_divergence
         cfg.seed = int(seed)
         cfg.n_particles = self.n
+        cfg.moving_average_update_rate = params.moving_average_update_rate
+        for o in range(self.n_obj):
+            for k in range(3):
+                cfg.centers[o][k] = float(self.centers[o, k])
         self._lib = sensor._lib
         self._h = C.c_void_p()
         abi.check(self._lib, self._lib.dbot_b200_filter_create(sensor._h, C.byref(cfg), C.byref(self._h)))
@@ -246,8 +319,9 @@ class DeviceParticleTracker:
         self.resample_count = 0
 
     def track(self, image):
+        """-> [n_obj][12], as ParticleTracker.track"""
         img = np.ascontiguousarray(image, dtype=np.float32).reshape(-1)
-        out = np.empty((self.n_obj, 6), dtype=np.float64)
+        out = np.empty((self.n_obj, 12), dtype=np.float64)
         cnt = self._C.c_int32(0)
         self._abi.check(self._lib, self._lib.dbot_b200_filter_track(self._h, self._abi.ptr(img), self._abi.ptr(out),
                                                                    self._C.byref(cnt)))

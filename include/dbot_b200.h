@@ -15,7 +15,8 @@
  *
  * Conventions: plain C types only; caller owns every host buffer; the library
  * owns all device memory and its CUDA stream; every call returns 0 on
- * success, <0 for argument errors, >0 for a CUDA error code; text through
+ * success, <0 for argument errors (-12: entry point not available on a multi-GPU handle, -13: reset() required
+ * after an update that failed on the device, -14: NCCL), >0 for a CUDA error code; text through
  * dbot_b200_last_error() (thread-local).  One caller at a time per handle
  * (the tracker serialises track() -- ref:source/dbot_ros/object_tracker_ros.hpp:111-125).
  * There is no CPU fallback: without a CUDA device create() fails.
@@ -31,6 +32,7 @@ extern "C" {
 
 #define DBOT_B200_ABI_VERSION 2
 #define DBOT_B200_MAX_OBJECTS 8
+#define DBOT_B200_MAX_DEVICES 8
 
 typedef struct dbot_b200_sensor dbot_b200_sensor; /* opaque */
 
@@ -56,7 +58,7 @@ typedef struct
     double p_occluded_visible, p_occluded_occluded,
         initial_occlusion_prob;                    /* ref:config/particle_tracker.yaml:41-43 */
     double delta_time;   /* ref:source/dbot_ros/tracker/particle_tracker_node.cpp:189 (1/30) */
-    int32_t device_id;   /* CUDA device ordinal of this handle (one handle per GPU) */
+    int32_t device_id;   /* CUDA device ordinal of a single-device handle (n_devices <= 1 and no device_ids) */
     int32_t occlusion_mode; /* 0 = dense: one full-frame fp32 occlusion image per particle with the
                                semantics of dbot's GPU evaluator (whole image propagated on every
                                update).  Other values are reserved. */
@@ -66,6 +68,16 @@ typedef struct
                                depth is unchanged); 1 = never: every triangle is drawn, as dbot's
                                RigidBodyRenderer does.  Open or inconsistently oriented meshes are always
                                drawn completely. */
+    int32_t n_devices;      /* 0 or 1: one GPU (device_id, or device_ids[0] when given).  2..8: the particles of
+                               every loglikes call -- and their occlusion slots -- are sharded over that many GPUs
+                               of this process; frame, mesh and camera are replicated; one all-gather of the
+                               log-weights per call over NVLink (BASELINE config 4).
+                               Results are bit-identical to a single-GPU handle. */
+    const int32_t* device_ids; /* [n_devices] CUDA ordinals, NULL = 0 .. n_devices-1 (an ordinal may repeat only
+                                  with gather_mode 1: shards then share that GPU) */
+    int32_t gather_mode;    /* n_devices > 1: 0 = ncclAllGather (libnccl.so.2 bound at run time), 1 = fused: the
+                               particle kernel stores each log-weight into every GPU's gathered vector through
+                               NVLink peer memory, no collective launch */
 } dbot_b200_config;
 
 /* RbSensorBuilder<State>::build() with use_gpu == true */
@@ -125,15 +137,30 @@ typedef struct
     double max_kl_divergence;                 /* ref:config/particle_tracker.yaml:36 */
     uint64_t seed;                            /* counter-based noise: same seed, same track */
     int32_t n_particles;                      /* evaluation_count / n_objects, <= max_particles */
+    double moving_average_update_rate;        /* ref:config/particle_tracker.yaml:25, in (0, 1]; 1 = no smoothing */
+    double centers[DBOT_B200_MAX_OBJECTS][3]; /* center_object_frame (ref:config/particle_tracker.yaml:30,
+                                                 ref:...particle_tracker_node.cpp:210-214): the offset by which
+                                                 every part's vertices were shifted (ObjectModel centers); poses
+                                                 cross this API in the MODEL frame and are converted on the way
+                                                 in and out.  Zeros when the meshes were not centred. */
 } dbot_b200_filter_config;
 int dbot_b200_filter_create(dbot_b200_sensor* s, const dbot_b200_filter_config* cfg, dbot_b200_filter** out);
 int dbot_b200_filter_destroy(dbot_b200_filter* f);
-/* poses: [n_objects][6] position + rotation vector in the camera frame; resets the sensor */
+/* poses: [n_objects][6] position + rotation vector of the model frame in the camera frame; resets the sensor */
 int dbot_b200_filter_initialize(dbot_b200_filter* f, const double* poses);
-/* out_poses: [n_objects][6] integrated poses after this frame; out_resamplings (optional): number of
- * resampling steps since initialize */
-int dbot_b200_filter_track(dbot_b200_filter* f, const float* depth_m, double* out_poses,
+/* out_states: [n_objects][12] the state the reference publishes after this frame
+ * (ref:source/dbot_ros/object_tracker_ros.hpp:49-61): position, rotation vector, linear and angular velocity,
+ * moving average applied, model frame; out_resamplings (optional): resampling steps since initialize */
+int dbot_b200_filter_track(dbot_b200_filter* f, const float* depth_m, double* out_states,
                            int32_t* out_resamplings);
+
+/* particle-sharded evaluation with one single-device handle per process (dbot_ros_b200/sharded.py): the update
+ * of a call in which this shard received no particle -- every slot is given back and the handle's update clock
+ * advances as on the other shards */
+int dbot_b200_update_empty(dbot_b200_sensor* s);
+/* number of GPUs behind the handle; occlusion slots that have moved between them since create */
+int dbot_b200_device_count(dbot_b200_sensor* s);
+int64_t dbot_b200_migrated_slots(dbot_b200_sensor* s);
 
 /* ---- state read-back (tests, debugging) ---- */
 int dbot_b200_n_slots(dbot_b200_sensor* s);

@@ -1,26 +1,23 @@
 #!/usr/bin/env python
-"""Offline replay harness (shape of the reference's unbuilt
-TrackingDataset / DataSetCameraDataProvider, ref:source/dbot_ros/util/tracking_dataset.cpp:92-101,176-285):
-depth frames + ground-truth poses in, tracking error + frames/s out.
+"""Offline replay harness, command line (the library part is dbot_ros_b200/replay.py).
 
-  tools/replay.py --synthetic [--config 2] [--frames 60] [--tracker device|host]
-  tools/replay.py --frames-npy depth.npy --truth-npy poses.npy --mesh a.obj [b.obj ...] --K fx fy cx cy
+  tools/replay.py --synthetic [--config 2] [--frames 60] [--tracker device|host] [--save-dataset DIR]
+  tools/replay.py --dataset DIR --mesh a.obj [b.obj ...] [--downsampling 1] [--center-object-frame]
 
-depth.npy: [F][rows][cols] float32 metres (NaN = no data); poses.npy: [F][n_obj][6] position + rotation
-vector; the first ground-truth pose (plus --init-offset) initialises the tracker, as the interactive
-marker does in the reference (ref:source/dbot_ros/tracker/particle_tracker_node.cpp:226-252)."""
+DIR holds ground_truth.txt in the reference's layout (ref:source/dbot_ros/util/tracking_dataset.cpp:325-357:
+"<stamp> <12 state values per object>" per line) and measurements.npz (depth [F][rows][cols] float32 metres,
+stamps [F], K [3][3]) standing in for measurements.bag, which needs ROS to read."""
 import argparse
 import json
 import os
 import sys
-import time
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from dbot_ros_b200 import CameraData, ObjectModel, Parameters, RbSensorBuilder, io, synth  # noqa: E402
-from dbot_ros_b200.tracker import DeviceParticleTracker, ParticleTracker, TrackerParameters  # noqa: E402
+from dbot_ros_b200 import CameraData, ObjectModel, Parameters, RbSensorBuilder, io, replay, synth  # noqa: E402
+from dbot_ros_b200.tracker import TrackerParameters  # noqa: E402
 
 
 def main():
@@ -30,10 +27,11 @@ def main():
     ap.add_argument("--frames", type=int, default=60)
     ap.add_argument("--particles", type=int, default=0)
     ap.add_argument("--tracker", default="device", choices=["device", "host"])
-    ap.add_argument("--frames-npy")
-    ap.add_argument("--truth-npy")
+    ap.add_argument("--dataset")
+    ap.add_argument("--save-dataset")
     ap.add_argument("--mesh", nargs="*")
-    ap.add_argument("--K", nargs=4, type=float)
+    ap.add_argument("--center-object-frame", action="store_true")
+    ap.add_argument("--moving-average-update-rate", type=float, default=1.0)
     ap.add_argument("--init-offset", type=float, default=0.004)
     ap.add_argument("--seed", type=int, default=1)
     a = ap.parse_args()
@@ -43,45 +41,30 @@ def main():
         rows, cols = synth.resolution(ds)
         K = synth.camera_matrix(ds)
         V, T = synth.mesh_set(mesh)
-        model = ObjectModel(V, T)
+        model = ObjectModel(V, T, center_object_frame=a.center_object_frame)
     else:
-        depth = np.load(a.frames_npy)
-        rows, cols = depth.shape[1:]
-        K = np.array([[a.K[0], 0, a.K[2]], [0, a.K[1], a.K[3]], [0, 0, 1.0]])
-        model = io.object_model_from_files("", a.mesh, center_object_frame=False)
+        d = io.load_dataset(a.dataset)
+        rows, cols = d["depth"].shape[1:]
+        K = d["K"]
+        model = io.object_model_from_files("", a.mesh, center_object_frame=a.center_object_frame)
         n = 1000
     n_obj = model.count_parts
     n = a.particles or n
     sensor = RbSensorBuilder(model, CameraData(K, rows, cols), Parameters(sample_count=n)).build()
+    prm = TrackerParameters(evaluation_count=n * n_obj, center_object_frame=a.center_object_frame,
+                            moving_average_update_rate=a.moving_average_update_rate)
+    kw = dict(tracker=a.tracker, params=prm, centers=model.centers, seed=a.seed, init_offset=a.init_offset)
     if a.synthetic:
-        gt0 = synth.ground_truth_poses(n_obj, rng)
-        start = np.array([np.concatenate([t, [0, 0, 0]]) for _, t in gt0])
-        vel = rng.normal(scale=[0.0015, 0.0015, 0.0015, 0.01, 0.01, 0.01], size=(n_obj, 6))
-        truth = np.stack([start + f * vel for f in range(a.frames)])
-        depth = np.stack([synth.make_frame(sensor.render, [(synth.rodrigues(p[3:6]), p[0:3]) for p in truth[f]],
-                                           rows, cols, rng, occluder=False) for f in range(a.frames)])
+        # frames are rendered with the un-centred meshes' poses: the model frame is what ground truth speaks
+        plain = sensor if not a.center_object_frame else RbSensorBuilder(
+            ObjectModel(V, T), CameraData(K, rows, cols), Parameters(sample_count=8)).build()
+        depth, stamps, states = replay.synthetic_sequence(plain.render, n_obj, rows, cols, a.frames, rng)
+        if a.save_dataset:
+            io.save_dataset(a.save_dataset, depth, stamps, K, states)
+        out, _ = replay.replay(sensor, depth, io.ground_truth_poses(states, n_obj), **kw)
     else:
-        truth = np.load(a.truth_npy)
-    prm = TrackerParameters(evaluation_count=n * n_obj)
-    tracker = (DeviceParticleTracker(sensor, prm, seed=a.seed) if a.tracker == "device"
-               else ParticleTracker(sensor, n_obj, prm, seed=a.seed))
-    init = truth[0].copy()
-    init[:, :3] += a.init_offset * np.array([1.0, -1.0, 1.0]) / np.sqrt(3.0)
-    tracker.initialize(init)
-    est, times = [], []
-    for f in range(len(depth)):
-        t0 = time.perf_counter()
-        est.append(tracker.track(depth[f]))
-        times.append(time.perf_counter() - t0)
-    est = np.array(est)
-    err = np.linalg.norm(est[:, :, :3] - truth[:, :, :3], axis=2)
-    warm = times[3:] if len(times) > 6 else times
-    print(json.dumps({"tracker": a.tracker, "frames": len(depth), "particles_per_block": n, "objects": n_obj,
-                      "resolution": [cols, rows], "position_error_mm": {"mean": 1e3 * float(err.mean()),
-                      "max": 1e3 * float(err.max()), "last": 1e3 * float(err[-1].max())},
-                      "ms_per_frame": 1e3 * float(np.mean(warm)), "fps": 1.0 / float(np.mean(warm)),
-                      "particle_likelihoods_per_s": n * n_obj / float(np.mean(warm)),
-                      "resamplings": int(tracker.resample_count)}))
+        out, _ = replay.replay_dataset(a.dataset, sensor, n_obj, **kw)
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":
