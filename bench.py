@@ -7,11 +7,15 @@ particles (ref:source/dbot_ros/object_tracker_ros.hpp:49 -> dbot filter, SURVEY.
 
   value   device-resident: frames, poses and parent indices already in HBM, the two kernels
           launched through the *_device C-ABI entry points, timed with CUDA events on the
-          library's stream.
-  e2e     the same step through the reference-facing host call (host numpy buffers in, host
-          log-weights out; H2D/D2H inside the timed region).
-  roofline  the fused particle kernel (update): algorithmic bytes = 8*P per particle (read the
-          parent's fp32 occlusion image, write the child's), launch duration from CUDA events.
+          library's stream.  The K timed steps are repeated REPEATS times; value is the median repeat.
+  e2e     the same step through the reference-facing host call with ordinary (pageable) host numpy
+          buffers in and host log-weights out -- what the C++ adapter hands over; H2D/D2H inside the
+          timed region.  e2e_pinned: the same from page-locked buffers.
+  roofline  the fused particle kernel (update).  achieved = the bytes the launch actually has to move
+          (copying children x 8P + covered pixels x 8 per particle) / launch duration from CUDA
+          events; frac_dram = DRAM bytes ncu counted for the same launch / duration / peak; the
+          dense-formulation figure of SURVEY.md 8(d) (8P per particle whether copied or not) is kept
+          beside it as dense_equivalent.  `bound` says what ncu shows limits the kernel.
   cpu_baseline / --impl reference   the CPU oracle (oracle/, lazily propagated occlusion state as in
           dbot's CPU model, OpenMP over particles, all host cores) on a bounded particle sample of
           the same frames.
@@ -35,6 +39,7 @@ METRIC = "particle-likelihoods/sec"  # BASELINE.json: "particle-likelihoods/sec 
 UNIT = "particle-likelihoods/s"
 CONFIG_ID = 2            # BASELINE.json configs[1]: 1000 particles, 640x480, single 5k-tri mesh
 N_FRAMES = 4             # distinct synthetic frames / pose sets cycled through the steps
+REPEATS = 5              # the K timed steps are run this many times; the median repeat is reported
 
 
 def workload(config_id=CONFIG_ID):
@@ -209,6 +214,43 @@ def run_reference(args):
     emit(line)
 
 
+def single_process_multi_gpu(w, world, n_per_gpu, gather_mode, frames, steps, warmup):
+    """BASELINE config 4's shape through ONE handle in ONE process (dbot_b200_config.n_devices, what a C++
+    RbSensorBuilder::build() returns): host buffers in, host log-weights out, particles sharded over `world`
+    GPUs inside the library, shard-local parents.  -> particle-likelihoods/s (wall clock, median of REPEATS)"""
+    n = n_per_gpu * world
+    sensor = RbSensorBuilder(ObjectModel(w["V"], w["T"]), CameraData(w["K"], w["rows"], w["cols"]),
+                             Parameters(sample_count=n), device_ids=list(range(world)), gather_mode=gather_mode).build()
+    rng = synth.rng_for(4)
+    gt = synth.ground_truth_poses(len(w["V"]), rng)
+    poses = [synth.particle_poses(gt, n, rng) for _ in range(2)]
+    parents = [np.concatenate([resampled_parents(n_per_gpu, rng) + g * n_per_gpu for g in range(world)]).astype(np.int32)
+               for _ in range(2)]
+    idx = np.zeros(n, dtype=np.int32)
+    sensor.set_observation(frames[0])
+    sensor.loglikes_poses(poses[0], idx, True)
+
+    def step(k):
+        idx[:] = parents[k % 2]
+        sensor.set_observation(frames[k % len(frames)])
+        return sensor.loglikes_poses(poses[k % 2], idx, True)
+
+    for k in range(warmup):
+        step(k)
+    secs = []
+    for _ in range(REPEATS):
+        t0 = time.perf_counter()
+        for k in range(steps):
+            step(k)
+        secs.append(time.perf_counter() - t0)
+    out = {"value": n * steps / float(np.median(secs)), "unit": UNIT, "particles_total": n, "n_gpus": world,
+           "gather": "ncclAllGather" if gather_mode == 0 else "fused peer stores from the kernel epilogue",
+           "fps": steps / float(np.median(secs)), "device_bytes": sensor.device_bytes,
+           "value_min": n * steps / max(secs), "value_max": n * steps / min(secs)}
+    sensor.close()
+    return out
+
+
 _REAL_STDOUT = None
 
 
@@ -309,19 +351,23 @@ def main():
     # per-kernel); a few tens of milliseconds of GPU work are too short for one loop alone
     clocks = ClockSampler(local_rank)
     clocks.__enter__()
-    ms = timed(device_step, args.steps)
-    gpu_launches = int(sensor.launch_count - launches0)
+    rep_ms = []
+    for _ in range(REPEATS):
+        rep_ms.append(timed(device_step, args.steps))
+    gpu_launches = int(sensor.launch_count - launches0) // REPEATS
+    ms = float(np.median(rep_ms))
     value = n * world * args.steps / (ms * 1e-3)
 
     # ---- e2e: host buffers through the reference-facing call ----
-    # the step's inputs start in page-locked host memory (the library copies straight from it)
+    # headline: ordinary pageable numpy arrays, as the C++ adapter's std::vector (the library stages them);
+    # e2e_pinned: the same from page-locked memory (the library copies straight from it)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
-    frames = [pin(f) for f in frames]
-    poses = [pin(q) for q in poses]
+    host_inputs = {"pageable": ([f.copy() for f in frames], [q.copy() for q in poses]),
+                   "pinned": ([pin(f) for f in frames], [pin(q) for q in poses])}
     idx_host = [p.copy() for p in parents]
     if world > 1:
-        # the public multi-GPU API: particle-sharded sensor, all-gather of log-weights inside the call.
-        # Every rank passes the global arrays; it reads only its own contiguous shard of them.
+        # the public multi-GPU API under torchrun: particle-sharded sensor, all-gather of log-weights inside
+        # the call.  Every rank passes the global arrays; it reads only its own contiguous shard of them.
         from dbot_ros_b200.sharded import ShardedRbSensor, shard_bounds
 
         sharded = ShardedRbSensor(sensor)
@@ -337,28 +383,38 @@ def main():
             g_parents.append(gi)
         g_idx = [g.copy() for g in g_parents]
 
-    def host_step(k):
-        f = k % N_FRAMES
-        if world > 1:
-            g_idx[f][:] = g_parents[f]
-            sharded.set_observation(frames[f])
-            return sharded.loglikes_poses(g_poses[f], g_idx[f], True)
-        idx_host[f][:] = parents[f]
-        sensor.set_observation(frames[f])
-        return sensor.loglikes_poses(poses[f], idx_host[f], True)
+    def run_e2e(kind):
+        fr, po = host_inputs[kind]
 
-    for k in range(args.warmup):
-        host_step(k)
-    sync_all()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        host_step(k)
-    sync_all()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        def host_step(k):
+            f = k % N_FRAMES
+            if world > 1:
+                g_idx[f][:] = g_parents[f]
+                sharded.set_observation(fr[f])
+                return sharded.loglikes_poses(g_poses[f], g_idx[f], True)
+            idx_host[f][:] = parents[f]
+            sensor.set_observation(fr[f])
+            return sensor.loglikes_poses(po[f], idx_host[f], True)
+
+        for k in range(args.warmup):
+            host_step(k)
+        secs = []
+        for _ in range(REPEATS):
+            sync_all()
+            t0 = time.perf_counter()
+            for k in range(args.steps):
+                host_step(k)
+            sync_all()
+            dt_s = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt_s], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt_s = float(t.item())
+            secs.append(dt_s)
+        return float(np.median(secs)), secs
+
+    e2e_s, e2e_all = run_e2e("pageable")
+    e2e_pin_s, _ = run_e2e("pinned")
     e2e = n * world * args.steps / e2e_s
     h2d = P * 4 + n * len(w["V"]) * 12 * 4 + n * 4
     d2h = n * 8
@@ -381,21 +437,39 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None
+    ncu = {}
     try:  # one ncu --set full capture of the same kernel and workload, committed under profiles/
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            ncu = json.load(f)
     except Exception:
         pass
-    alg_bytes = 8.0 * P * n                       # 4P read + 4P written per particle
+    traffic = ncu.get("dram_bytes_per_launch")
     avg_ms = k_ms / max(k_cnt, 1)
+    # what this launch has to move: a child that does not adopt its parent's slot reads and writes a whole
+    # image (8P); every particle reads the parent's value and writes the posterior at its covered pixels
+    copies = float(np.mean([len(p) - len(np.unique(p)) for p in parents]))
+    sample = poses[0][:: max(1, n // 16)][:16]
+    n_cov = float(np.mean([np.isfinite(sensor.render(q)).sum() for q in sample]))
+    alg_bytes = copies * 8.0 * P + n * 8.0 * n_cov
+    dense_bytes = 8.0 * P * n                     # SURVEY.md 8(d), dense formulation: 4P read + 4P written per particle
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "dbot_particle_kernel<UPDATE>", "achieved": achieved,
+    frac_dram = (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic else None
+    issue_pct = ncu.get("issue_active_pct")
+    # the kernel is HBM-bound only if DRAM is what ncu shows busy; otherwise it is bound by instruction issue
+    bound = "hbm" if (frac_dram is not None and frac_dram >= 0.5) else "issue"
+    roofline = {"bound": bound, "kernel": "dbot_particle_kernel<UPDATE>", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu dram__bytes_read.sum + "
-                "dram__bytes_write.sum, one launch)" if traffic else None,
+                "traffic": traffic, "frac_dram": frac_dram,
+                "traffic_source": "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one "
+                                  "launch of the same workload)" if traffic else None,
+                "issue_active_pct_ncu": issue_pct,
                 "algorithmic_bytes_per_launch": alg_bytes,
+                "algorithmic_bytes": "copying children (%.0f of %d) x 8P + %d covered pixels x 8 B x %d particles"
+                                     % (copies, n, round(n_cov), n),
+                "dense_equivalent": {"bytes_per_launch": dense_bytes, "GBps": dense_bytes / (avg_ms * 1e-3) / 1e9,
+                                     "frac": dense_bytes / (avg_ms * 1e-3) / 1e9 / peak,
+                                     "note": "8P per particle whether copied or not (SURVEY.md 8d); not a DRAM rate"},
                 "avg_launch_ms": avg_ms, "launches_timed": k_cnt,
                 "kernel_share_of_step": k_ms / max(k_ms + o_ms + p_ms, 1e-9),
                 "observation_kernel_avg_ms": o_ms / max(o_cnt, 1),
@@ -405,8 +479,13 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": describe(w, world), "fps": args.steps / (ms * 1e-3),
+            "repeats": {"count": REPEATS, "steps_each": args.steps, "ms_per_step": [m / args.steps for m in rep_ms],
+                        "value_min": n * world * args.steps / (max(rep_ms) * 1e-3),
+                        "value_max": n * world * args.steps / (min(rep_ms) * 1e-3), "reported": "median"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "fps": args.steps / e2e_s},
+                    "fps": args.steps / e2e_s, "host_buffers": "pageable",
+                    "value_min": n * world * args.steps / max(e2e_all), "value_max": n * world * args.steps / min(e2e_all)},
+            "e2e_pinned": {"value": n * world * args.steps / e2e_pin_s, "unit": UNIT, "host_buffers": "page-locked"},
             "gpu_launches": gpu_launches, "clocks": clocks.summary(), "roofline": roofline}
 
     if rank == 0 and world == 1:
@@ -442,6 +521,26 @@ def main():
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "%d of the %d particles per step, %d steps (%.1f s of CPU work), same "
                                           "frames, OpenMP over particles" % (sample, n, reps, sec * reps)}
+    if world > 1:
+        # multi-GPU behind the C-ABI (one process, one handle): measured by rank 0 alone while the other ranks
+        # wait with idle GPUs.  Weak-scaled config 2 (comparable with this line's value) and, on 8 GPUs or with
+        # DBOT_BENCH_CONFIG4=1, BASELINE config 4 at its stated size (8 x 10 000 = 80 000 particles).
+        sync_all()
+        if rank == 0:
+            sp = {}
+            try:
+                for name, mode in (("nccl", 0), ("fused", 1)):
+                    sp["config2_per_gpu_%s" % name] = single_process_multi_gpu(w, world, n, mode, frames, args.steps,
+                                                                               args.warmup)
+                if world == 8 or os.environ.get("DBOT_BENCH_CONFIG4") == "1":
+                    n4 = synth.CONFIGS[4][1]
+                    for name, mode in (("nccl", 0), ("fused", 1)):
+                        sp["config4_%s" % name] = single_process_multi_gpu(w, world, n4, mode, frames,
+                                                                           max(4, args.steps // 4), 3)
+            except Exception as e:  # the bench line does not depend on it
+                sp["error"] = str(e)
+            line["single_process"] = sp
+        dist.barrier()
     if rank == 0:
         emit(line)
     if world > 1:

@@ -14,19 +14,17 @@
  *    per warp (ballot + popc); the few triangles that do not fit a batch lane (more than
  *    DBOT_SPAN_BATCH_ROWS rows, or int64 edge functions) go to the back of the same list.
  * 2. set-up (a warp takes 32 survivors at a time, one per lane): plane equation bit for bit as the
- *    oracle, the three edges sorted into long / short as dbot_setup_spans describes, one 80-byte
- *    span record per triangle in the warp's record buffer.
+ *    oracle, the three edges sorted into long / short as dbot_setup_spans describes; the span record
+ *    stays in the lane's registers.
  * 3. units: the pixel rows of the 32 triangles are dealt out evenly over the lanes -- unit q of the
  *    batch is row q - first_row(owner) of its owner, the owner being found from a 1024-bit mask of
- *    first rows (one word per lane) by two shuffles and a popc.  A unit reads its owner's record
- *    (four conflict-free LDS), computes the exact first and last covered column of its row
+ *    first rows (one word per lane) by two shuffles and a popc.  A unit fetches its owner's record
+ *    by shuffle, computes the exact first and last covered column of its row
  *    (dbot_row_span) and sends only those pixels' inverse depths to the tile's max
  *    (red.shared.max on the bits of the positive float).  No pixel outside a triangle is ever
  *    tested: 35 k fragments and 15 k row units per particle for the 5120-triangle mesh, where the
  *    block sweep of round 1 tested 385 k pixels.                                              */
 #define DBOT_BOX_CHUNKS 32 /* chunks beyond this many are never culled against a tile */
-#define DBOT_REC_WORDS 20  /* span record: five 16-byte quarters; a stride of 20 words keeps the
-                              quarter loads of up to 8 different records in a phase conflict-free */
 #define DBOT_LIST_WIDE 0x8000u /* flag in the survivor list: int64 block walk instead of span units */
 
 __device__ __forceinline__ void dbot_zmax(uint32_t* p, uint32_t v)
@@ -40,7 +38,6 @@ struct dbot_raster_smem
     const float4* v4;     /* [nv] camera-frame x, y, z and 1/z */
     const int2* XY;       /* [nv] snapped image position */
     uint16_t* list;       /* [ntri] survivors from the front, tall / wide triangles from the back */
-    uint32_t* rec;        /* this warp's record buffer, 32 x DBOT_REC_WORDS words */
     uint32_t* mask;       /* this warp's first-row mask, 32 words */
     uint32_t* wt;         /* inverse-depth tile */
     int* counters;        /* [0] survivors, [1] tall + wide, [2] next batch */
@@ -80,6 +77,7 @@ __device__ __forceinline__ void dbot_raster_prepass(const dbot_raster_smem& S, i
             if (m_front) b_front = atomicAdd(&S.counters[0], __popc(m_front));
             if (m_back) b_back = atomicAdd(&S.counters[1], __popc(m_back));
         }
+        __syncwarp();
         b_front = __shfl_sync(DBOT_FULL, b_front, 0);
         b_back = __shfl_sync(DBOT_FULL, b_back, 0);
         if (kind == DBOT_TRI_SPANS)
@@ -90,51 +88,52 @@ __device__ __forceinline__ void dbot_raster_prepass(const dbot_raster_smem& S, i
     }
 }
 
-/* one (triangle, row) unit: record at `rec` (shared-memory byte address), row j of its box;
- * pa = first unit of the owner | aux << 11 (dbot_span_rec::aux) */
-__device__ __forceinline__ void dbot_span_unit(uint32_t rec, int j, int aux, bool active, uint32_t tile_s,
-                                               int row0, int col0, int ww)
+/* one (triangle, row) unit: row j of the box of the triangle whose span record the lane `owner` holds in its
+ * registers (s); every field the unit needs comes over by shuffle -- the records never touch shared memory,
+ * which leaves it to the z tile (a 5120-triangle particle's whole window fits one tile) */
+__device__ __forceinline__ void dbot_span_unit(const dbot_span_rec& s, int owner, int j, int aux, bool active,
+                                               uint32_t tile_s, uint32_t dummy_s, int row0, int col0, int ww)
 {
     const int bwm1 = aux & 0xff, split = (aux >> 8) & 0xff;
-    const bool long_left = (aux >> 16) & 1;
-    const uint32_t short_q = rec + (j >= split ? 32u : 16u);
-    const uint32_t left_q = long_left ? rec : short_q, right_q = long_left ? short_q : rec;
+    const bool long_left = (aux >> 16) & 1, lower = j >= split;
+    /* long edge, and the short edge that bounds this row on the other side */
+    const int a0 = __shfl_sync(DBOT_FULL, s.A.g0, owner), a1 = __shfl_sync(DBOT_FULL, s.A.gr, owner),
+              a2 = __shfl_sync(DBOT_FULL, s.A.gc, owner);
+    const int u0 = __shfl_sync(DBOT_FULL, s.B1.g0, owner), u1 = __shfl_sync(DBOT_FULL, s.B1.gr, owner),
+              u2 = __shfl_sync(DBOT_FULL, s.B1.gc, owner);
+    const int v0 = __shfl_sync(DBOT_FULL, s.B2.g0, owner), v1 = __shfl_sync(DBOT_FULL, s.B2.gr, owner),
+              v2 = __shfl_sync(DBOT_FULL, s.B2.gc, owner);
+    const float m0 = __shfl_sync(DBOT_FULL, s.m0, owner), m1 = __shfl_sync(DBOT_FULL, s.m1, owner),
+                m2 = __shfl_sync(DBOT_FULL, s.m2, owner);
+    const float wlo = __shfl_sync(DBOT_FULL, s.wlo, owner), whi = __shfl_sync(DBOT_FULL, s.whi, owner);
+    const int org = __shfl_sync(DBOT_FULL, s.org, owner);
+    const int b0 = lower ? v0 : u0, b1 = lower ? v1 : u1, b2 = lower ? v2 : u2;
     dbot_edge L, R;
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(L.g0), "=r"(L.gr), "=r"(L.gc), "=f"(L.nrc) : "r"(left_q));
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(R.g0), "=r"(R.gr), "=r"(R.gc), "=f"(R.nrc) : "r"(right_q));
-    float m0, m1, m2, wlo, whi;
-    int org;
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4+48];" : "=f"(m0), "=f"(m1), "=f"(m2), "=r"(org) : "r"(rec));
-    asm volatile("ld.shared.v2.b32 {%0,%1}, [%2+64];" : "=f"(wlo), "=f"(whi) : "r"(rec));
+    L.g0 = long_left ? a0 : b0; L.gr = long_left ? a1 : b1; L.gc = long_left ? a2 : b2;
+    R.g0 = long_left ? b0 : a0; R.gr = long_left ? b1 : a1; R.gc = long_left ? b2 : a2;
+    L.nrc = -dbot_rcp_fast((float)L.gc); /* estimates only: dbot_row_span corrects them exactly */
+    R.nrc = -dbot_rcp_fast((float)R.gc);
     int first;
     int n = dbot_row_span(L, R, j, bwm1, first);
-    if (!active) n = 0;
-    if (n > 0)
+    if (!active || n < 0) n = 0;
+    const int r = (org >> 16) + j, c = (org & 0xffff) + first;
+    const float wr = dbot_fmaf(m1, (float)r, m2);
+    float fc = (float)c;
+    uint32_t addr = tile_s + 4u * (uint32_t)((r - row0) * ww + (c - col0));
+    /* The pixel loop runs the same number of times in every lane (the longest span of the round): a lane
+     * whose span is done sends its inverse depths to its own dummy word instead.  A data-dependent trip count
+     * would make this a divergent loop around an atomic, which the compiler must treat as a potential spin
+     * lock (YIELD in the loop: lanes that finish early are released from the reconvergence point and run the
+     * rest of the round as separate groups -- measured: half the lanes idle through the whole unit loop). */
+    const int nmax = __reduce_max_sync(DBOT_FULL, n);
+    for (int k = 0; k < nmax; ++k)
     {
-        const int r = (org >> 16) + j, c = (org & 0xffff) + first;
-        const float wr = dbot_fmaf(m1, (float)r, m2);
-        float fc = (float)c;
-        uint32_t addr = tile_s + 4u * (uint32_t)((r - row0) * ww + (c - col0));
-        do
-        {
-            const uint32_t bits = dbot_f2u(fminf(fmaxf(dbot_fmaf(m0, fc, wr), wlo), whi));
-            asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(addr), "r"(bits) : "memory");
-            fc = dbot_add(fc, 1.0f);
-            addr += 4u;
-        } while (--n);
+        const uint32_t bits = dbot_f2u(fminf(fmaxf(dbot_fmaf(m0, fc, wr), wlo), whi));
+        const uint32_t a = k < n ? addr : dummy_s;
+        asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(a), "r"(bits) : "memory");
+        fc = dbot_add(fc, 1.0f);
+        addr += 4u;
     }
-}
-
-__device__ __forceinline__ void dbot_store_record(uint32_t* dst, const dbot_span_rec& s)
-{
-    uint4* q = reinterpret_cast<uint4*>(dst);
-    q[0] = make_uint4((uint32_t)s.A.g0, (uint32_t)s.A.gr, (uint32_t)s.A.gc, __float_as_uint(s.A.nrc));
-    q[1] = make_uint4((uint32_t)s.B1.g0, (uint32_t)s.B1.gr, (uint32_t)s.B1.gc, __float_as_uint(s.B1.nrc));
-    q[2] = make_uint4((uint32_t)s.B2.g0, (uint32_t)s.B2.gr, (uint32_t)s.B2.gc, __float_as_uint(s.B2.nrc));
-    q[3] = make_uint4(__float_as_uint(s.m0), __float_as_uint(s.m1), __float_as_uint(s.m2), (uint32_t)s.org);
-    q[4] = make_uint4(__float_as_uint(s.wlo), __float_as_uint(s.whi), (uint32_t)s.aux, 0u);
 }
 
 /* steps 2 and 3; called by every compute warp after the prepass has been published */
@@ -143,7 +142,9 @@ __device__ __forceinline__ void dbot_raster_sweep(const dbot_raster_smem& S, int
 {
     const int ww = col1 - col0 + 1;
     const uint32_t tile_s = smem_u32(S.wt);
-    const uint32_t rec_s = smem_u32(S.rec);
+    /* per-lane dummy words for finished spans: the warp's first-row mask, which is dead while the units run
+     * and rewritten at the start of the next batch (one word per lane: no bank conflict) */
+    const uint32_t dummy_s = smem_u32(S.mask + lane);
     const int n_front = S.counters[0], n_back = S.counters[1];
     const int front_batches = (n_front + 31) >> 5;
     const unsigned le = 0xffffffffu >> (31 - lane);
@@ -151,6 +152,7 @@ __device__ __forceinline__ void dbot_raster_sweep(const dbot_raster_smem& S, int
     {
         int batch = 0;
         if (lane == 0) batch = atomicAdd(&S.counters[2], 1);
+        __syncwarp();
         batch = __shfl_sync(DBOT_FULL, batch, 0);
         if (batch >= front_batches + n_back) break;
 
@@ -192,8 +194,10 @@ __device__ __forceinline__ void dbot_raster_sweep(const dbot_raster_smem& S, int
             continue;
         }
 
-        /* ---- set-up: one triangle per lane -> span record in the warp's buffer ---- */
+        /* ---- set-up: one triangle per lane -> span record in the lane's registers ---- */
         int nrows = 0, aux = 0;
+        dbot_span_rec s;
+        memset(&s, 0, sizeof(s));
         if (t >= 0)
         {
             const dbot_vertex a = dbot_load_vertex(S, S.tri[3 * t]), b = dbot_load_vertex(S, S.tri[3 * t + 1]),
@@ -202,9 +206,7 @@ __device__ __forceinline__ void dbot_raster_sweep(const dbot_raster_smem& S, int
             int rmin = dbot_ceil_subpix(dbot_min3(a.Y, b.Y, c.Y)), rmax = dbot_floor_subpix(dbot_max3(a.Y, b.Y, c.Y));
             cmin = max(cmin, col0); cmax = min(cmax, col1);
             rmin = max(rmin, row0); rmax = min(rmax, row1);
-            dbot_span_rec s;
             dbot_setup_spans(a, b, c, K, cmin, cmax, rmin, rmax, s);
-            dbot_store_record(S.rec + DBOT_REC_WORDS * lane, s);
             nrows = rmax - rmin + 1;
             aux = s.aux;
         }
@@ -244,10 +246,9 @@ __device__ __forceinline__ void dbot_raster_sweep(const dbot_raster_smem& S, int
              * owner of unit q is the number of first-row bits at or below q, minus one */
             const int owner = min(pre + __popc(w & le) - 1, 31);
             const int opa = __shfl_sync(DBOT_FULL, pa, owner);
-            dbot_span_unit(rec_s + 4u * DBOT_REC_WORDS * (uint32_t)owner, q - (opa & 0x7ff), opa >> 11, q < H, tile_s,
-                           row0, col0, ww);
+            dbot_span_unit(s, owner, q - (opa & 0x7ff), opa >> 11, q < H, tile_s, dummy_s, row0, col0, ww);
         }
-        __syncwarp(); /* the record buffer is rewritten by the next batch */
+        __syncwarp(); /* the dummy words (first-row mask) are rewritten by the next batch */
     }
 }
 
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
     __shared__ int s_cnt[4];                     /* raster pass: survivors, tall + wide, next batch */
     __shared__ uint32_t s_mask[DBOT_CW][32];     /* first-row masks of the span batches, per warp */
     __shared__ double s_red[DBOT_CW];
+    __shared__ int s_copied;                     /* update: copies this CTA's streaming warps have finished */
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -277,12 +279,20 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
     {
         mbar_init(&s_bar, 1);
         mbar_fence_init();
+        s_copied = 0;
     }
     __syncthreads();
 
     /* ================= streaming warps (update launches only) =================
      * A child that does not adopt its parent's slot (see dbot_plan_update_kernel) starts as a bit
-     * copy of the parent's stored image; propagation is applied lazily (dbot_b200_sensor::A). */
+     * copy of the parent's stored image; propagation is applied lazily (dbot_b200_sensor::A).
+     * The stream runs free: every destination is a fresh slot nobody else touches, so the copies of
+     * this CTA's later particles start as soon as the earlier ones are done, however far the compute
+     * warps are behind -- the HBM traffic of the launch is spread over its whole duration instead of
+     * being demanded particle by particle.  After each copy the stream (a) counts it in s_copied, which
+     * is what the compute warps of that particle wait for before they touch the child's slot, and
+     * (b) signs the parent off (pending): the compute warps read the child's own copy, never the
+     * parent, so a sibling that adopts the parent's slot is held up by copies only. */
     if (MODE == DBOT_MODE_UPDATE && warp >= DBOT_CW)
     {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DBOT_STREAM_REGS));
@@ -311,6 +321,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                              : "memory");
         };
         bool first = true;
+        int done = 0;
         for (int k = blockIdx.x; k < p.n; k += gridDim.x)
         {
             const int4 pl = p.plan[p.order[k]];
@@ -356,10 +367,16 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                         if (q < n8) stg256_stream(out + ((size_t)q << 3), v[u]);
                     }
                 }
+                __threadfence(); /* this thread's part of the copy is visible device-wide */
+                stream_sync();   /* ... and so is everybody else's */
+                if (sl == 0)
+                {
+                    atomicSub(p.pending + pl.z, 1); /* one reader of the parent's slot less */
+                    ++done;
+                    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(&s_copied)), "r"(done)
+                                 : "memory");
+                }
             }
-            role_arrive(DBOT_BAR_COPIED);
-            /* at most one particle ahead: wait until the compute warps have taken this copy */
-            role_sync(DBOT_BAR_CONSUMED);
         }
         return;
     }
@@ -375,7 +392,6 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
     S.v4 = s_v4;
     S.XY = s_XY;
     S.list = (uint16_t*)(smem + p.off_list);
-    S.rec = (uint32_t*)(smem + p.off_rec) + 32 * DBOT_REC_WORDS * warp;
     S.mask = s_mask[warp];
     S.wt = s_wt;
     S.counters = s_cnt;
@@ -423,9 +439,10 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
         }
     };
 
+    int my_copies = 0; /* update: copying children this CTA's compute warps have met so far */
     for (int k = blockIdx.x; k < p.n; k += gridDim.x)
     {
-        /* update launches walk the particles in the planned order (copying children first) */
+        /* update launches walk the particles in the planned order */
         const int i = (MODE == DBOT_MODE_UPDATE) ? p.order[k] : k;
         const float* pose = p.poses + (size_t)i * 12 * p.n_obj;
         int4 pl = make_int4(0, 0, 0, 0);
@@ -447,10 +464,12 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
             }
             continue;
         }
-        /* stored occlusion values are read from the parent's slot; an adopting sibling leaves it
-         * alone until this particle has signed off (pending count, end of the particle) */
-        const float* occ_in = p.pool + (size_t)pl.x * p.slot_stride;
+        /* stored occlusion values: the parent's slot, or -- a copying child of an update -- the child's own
+         * copy of it (ready once the streaming warps have counted it in s_copied) */
         float* occ_out = (MODE == DBOT_MODE_UPDATE) ? p.pool + (size_t)pl.y * p.slot_stride : nullptr;
+        const float* occ_in = (MODE == DBOT_MODE_UPDATE) ? occ_out : p.pool + (size_t)pl.x * p.slot_stride;
+        const bool copier = MODE == DBOT_MODE_UPDATE && pl.x != pl.y;
+        const int copy_idx = copier ? my_copies++ : 0;
 
 #ifdef DBOT_DBG_TIMELINE
         long long tl[8];
@@ -520,31 +539,36 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
         float acc = 0.0f;
         bool copied = false; /* update: this particle's slot is ready for the posterior */
         auto await_slot = [&]() {
-            /* a copying child: its slot holds the parent's image once the streaming warps arrive.
-             * An adopting child owns the parent's slot itself and waits until all its siblings are
-             * done reading it (they sign off at the end of their particle). */
-            role_sync(DBOT_BAR_COPIED);
-            role_arrive(DBOT_BAR_CONSUMED);
-            if (pl.x == pl.y)
+            /* a copying child: its slot holds the parent's image once the streaming warps have counted the
+             * copy.  An adopting child owns the parent's slot itself and waits until every copy of it has
+             * been taken (pending).  Neither wait depends on anything that waits itself, so both end; the
+             * bound (about a second) only turns a scheduling accident into an error code instead of a hung
+             * GPU. */
+            if (tid == 0)
             {
-                if (tid == 0)
+                int spins = 0;
+                for (;;)
                 {
-                    /* siblings never wait for anything, so this ends; the bound (about a second) only
-                     * turns a scheduling accident into an error code instead of a hung GPU */
-                    int spins = 0;
-                    while (atomicAdd(p.pending + pl.z, 0) > 0)
+                    int ready;
+                    if (copier)
                     {
-                        __nanosleep(200);
-                        if (++spins > (1 << 22))
-                        {
-                            atomicExch(p.err_flag, 3);
-                            break;
-                        }
+                        int c;
+                        asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(c) : "r"(smem_u32(&s_copied)) : "memory");
+                        ready = c > copy_idx;
                     }
-                    __threadfence();
+                    else
+                        ready = atomicAdd(p.pending + pl.z, 0) <= 0;
+                    if (ready) break;
+                    __nanosleep(copier ? 64 : 200);
+                    if (++spins > (1 << 22))
+                    {
+                        atomicExch(p.err_flag, 3);
+                        break;
+                    }
                 }
-                compute_sync();
+                __threadfence();
             }
+            compute_sync();
             copied = true;
         };
 
@@ -560,6 +584,9 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                 tile_rows = wh;
                 tile_cols = (int)(p.wcap / (uint32_t)wh);
             }
+            /* as few tiles as the capacity allows, of equal size: every tile costs a prepass over the mesh */
+            tile_rows = (wh + (wh + tile_rows - 1) / tile_rows - 1) / ((wh + tile_rows - 1) / tile_rows);
+            tile_cols = (ww + (ww + tile_cols - 1) / tile_cols - 1) / ((ww + tile_cols - 1) / tile_cols);
             for (int rb0 = r0; rb0 <= r1; rb0 += tile_rows)
             for (int cb0 = wc0; cb0 <= wc1; cb0 += tile_cols)
             {
@@ -615,61 +642,75 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                 }
                 else
                 {
+                    /* The tile is one flat array (row-major over the tile's own width): a warp takes 32 x
+                     * DBOT_UNIT_PX consecutive entries at a time, whatever rows they fall in -- no lane idles
+                     * because a row ended.  Row and column come back from the flat index by a multiply-high
+                     * with floor(2^32 / ww) + 1 (exact for these sizes: index * ww < 2^32; a tile one column wide is
+                     * its own case, 2^32 does not fit the multiplier). */
                     struct unit
                     {
                         uint32_t wb[DBOT_UNIT_PX];
                         float4 tab[DBOT_UNIT_PX];
                         float o_in[DBOT_UNIT_PX];
-                        size_t g; /* element offset of the unit's first column in the state / table */
+                        uint32_t g[DBOT_UNIT_PX]; /* element offset of the pixel in the state / table */
                     };
-                    auto fetch = [&](int r, int cb, unit& u) {
-                        uint32_t* wrow = s_wt + (r - rb0) * ww + cb + lane;
-                        u.g = (size_t)r * p.pitch + c0 + cb + lane;
+                    const int npx = (rb1 - rb0 + 1) * ww;
+                    const uint32_t inv_ww = ww > 1 ? 0xffffffffu / (uint32_t)ww + 1u : 0u;
+                    const uint32_t g0 = (uint32_t)rb0 * (uint32_t)p.pitch + (uint32_t)c0;
+                    auto fetch = [&](int base, unit& u) {
 #pragma unroll
                         for (int j = 0; j < DBOT_UNIT_PX; ++j)
-                            u.wb[j] = (cb + 32 * j + lane < ww) ? wrow[32 * j] : DBOT_W_EMPTY;
+                        {
+                            const int q = base + 32 * j + lane;
+                            u.wb[j] = q < npx ? s_wt[q] : DBOT_W_EMPTY;
+                            const uint32_t rr = ww > 1 ? __umulhi((uint32_t)q, inv_ww) : (uint32_t)q;
+                            u.g[j] = g0 + rr * (uint32_t)p.pitch + ((uint32_t)q - rr * (uint32_t)ww);
+                        }
 #pragma unroll
                         for (int j = 0; j < DBOT_UNIT_PX; ++j)
+                        {
+                            u.tab[j] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+                            u.o_in[j] = 0.f;
                             if (u.wb[j] != DBOT_W_EMPTY)
                             {
-                                wrow[32 * j] = DBOT_W_EMPTY; /* hand the tile back empty */
-                                u.tab[j] = __ldg(p.tab + u.g + 32 * j);
+                                s_wt[base + 32 * j + lane] = DBOT_W_EMPTY; /* hand the tile back empty */
+                                u.tab[j] = __ldg(p.tab + u.g[j]);
                                 /* update launches may read a slot whose covered pixels were written
                                  * in an earlier launch phase by its adopter-to-be: L2-coherent, not .nc */
-                                u.o_in[j] = (MODE == DBOT_MODE_UPDATE) ? __ldcg(occ_in + u.g + 32 * j)
-                                                                       : __ldg(occ_in + u.g + 32 * j);
+                                u.o_in[j] = (MODE == DBOT_MODE_UPDATE) ? __ldcg(occ_in + u.g[j]) : __ldg(occ_in + u.g[j]);
                             }
+                        }
                     };
                     auto evaluate = [&](const unit& u) {
+                        /* straight-line code for all DBOT_UNIT_PX pixels of the unit: a lane without a covered,
+                         * observed pixel computes on whatever it holds and the result is dropped by a select, so
+                         * that the four pixels' dependency chains (two MUFU.EX2, two MUFU.RCP, MUFU.LG2 each)
+                         * interleave instead of running one basic block after the other */
 #pragma unroll
                         for (int j = 0; j < DBOT_UNIT_PX; ++j)
-                            if (u.wb[j] != DBOT_W_EMPTY && u.tab[j].x == u.tab[j].x)
-                            {
-                                float o_new;
-                                /* the correctly rounded reciprocal, not MUFU alone: the oracle's
-                                 * (and dbot's) predicted depth is the float the renderer stores, and
-                                 * d - y cancels -- one ulp of d is 1e-5 in the Gaussian's argument */
-                                acc = dbot_add(acc, dbot_pixel_term(dbot_rcp(dbot_u2f(u.wb[j])), u.tab[j],
-                                                                    u.o_in[j], p.M, o_new));
-                                if (MODE == DBOT_MODE_UPDATE)
-                                    __stcs(occ_out + u.g + 32 * j, dbot_mul(dbot_sub(o_new, p.post_b), p.post_inv_a));
-                            }
-                    };
-#ifdef DBOT_DBG_NO_PIXELS
-                    if (p.n == 0x7654321)
-#endif
-                    for (int r = rb0 + warp; r <= rb1; r += DBOT_CW)
-                        for (int cb = 0; cb < ww; cb += 32 * DBOT_UNIT_PX)
                         {
-                            unit ua;
-                            fetch(r, cb, ua);
-                            evaluate(ua);
+                            const bool valid = u.wb[j] != DBOT_W_EMPTY && u.tab[j].x == u.tab[j].x;
+                            float o_new;
+                            /* the correctly rounded reciprocal, not MUFU alone: the oracle's (and dbot's)
+                             * predicted depth is the float the renderer stores, and d - y cancels -- one ulp
+                             * of d is 1e-5 in the Gaussian's argument */
+                            const float d = dbot_rcp_normal(dbot_u2f(valid ? u.wb[j] : 0x3f800000u));
+                            const float term = dbot_pixel_term(d, u.tab[j], u.o_in[j], p.M, o_new);
+                            acc = dbot_add(acc, valid ? term : 0.0f);
+                            if (MODE == DBOT_MODE_UPDATE && valid)
+                                __stcs(occ_out + u.g[j], dbot_mul(dbot_sub(o_new, p.post_b), p.post_inv_a));
                         }
+                    };
+                    for (int base = warp * (32 * DBOT_UNIT_PX); base < npx; base += DBOT_CW * 32 * DBOT_UNIT_PX)
+                    {
+                        unit ua;
+                        fetch(base, ua);
+                        evaluate(ua);
+                    }
                 }
             }
         }
-        if (MODE == DBOT_MODE_UPDATE && !copied) await_slot();
-        DBOT_TL(); /* this warp's mixture done */
+        DBOT_TL(); /* this warp's mixture done (a particle without a window writes nothing: no wait for its slot) */
 
         /* ---- one log-weight per particle: fixed shuffle tree, double across warps ---- */
         if (MODE != DBOT_MODE_RENDER)
@@ -696,15 +737,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                            MODE, i, tl[1] - tl[0], tl[2] - tl[1], tl[3] - tl[2], tl[4] - tl[3], tl[5] - tl[4],
                            tl[6] - tl[5], tl[6] - tl[0]);
 #endif
-                if (MODE == DBOT_MODE_UPDATE)
-                {
-                    p.indices[i] = i;
-                    if (pl.x != pl.y) /* done with the parent's slot: its adopter may write into it */
-                    {
-                        __threadfence();
-                        atomicSub(p.pending + pl.z, 1);
-                    }
-                }
+                if (MODE == DBOT_MODE_UPDATE) p.indices[i] = i;
             }
         }
     }

@@ -53,17 +53,10 @@ __device__ __forceinline__ void compute_sync()
 {
     asm volatile("bar.sync 1, %0;" ::"n"(DBOT_CT) : "memory");
 }
-/* producer/consumer hand-off between the streaming and the compute warps on hardware named
- * barriers (no polling): the producer side arrives, the consumer side syncs */
-#define DBOT_BAR_COPIED 2
-#define DBOT_BAR_CONSUMED 3
-__device__ __forceinline__ void role_arrive(int id)
+/* barrier among the streaming warps only */
+__device__ __forceinline__ void stream_sync()
 {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(DBOT_CT + DBOT_ST) : "memory");
-}
-__device__ __forceinline__ void role_sync(int id)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(DBOT_CT + DBOT_ST) : "memory");
+    asm volatile("bar.sync 2, %0;" ::"n"(DBOT_ST) : "memory");
 }
 __device__ __forceinline__ void ldg256(const float* p, float (&v)[8])
 {

@@ -161,13 +161,25 @@ __global__ void __launch_bounds__(DBOT_PLAN_THREADS, 1)
         if (ok && last[par] == i)
         {
             pl = make_int4(loc[par], loc[par], par, 0);
-            order[n_copies + arank++] = i;
+#ifdef DBOT_ORDER_COPIES_FIRST
+            order[n_copies + arank] = i;
+#endif
+            ++arank;
         }
         else
         {
             pl = make_int4(ok ? loc[par] : -1, free_stack[f0 - 1 - crank], ok ? par : 0, 0);
-            order[crank++] = i;
+#ifdef DBOT_ORDER_COPIES_FIRST
+            order[crank] = i;
+#endif
+            ++crank;
         }
+#ifndef DBOT_ORDER_COPIES_FIRST
+        /* the caller's order: copying and adopting children alternate as resampling left them, so that the
+         * copy stream's HBM traffic is spread over the whole launch; a parent's copies sit just before its
+         * adopter and are taken by the neighbouring CTAs' free-running streams */
+        order[i] = i;
+#endif
         plan[i] = pl;
         loc_next[i] = pl.y;
     }

@@ -8,7 +8,8 @@
  *
  * It needs dbot's own headers (dbot/model/rb_sensor.h, dbot/pose/*) and Eigen, none of which exist in
  * this repository's build image; tests/test_adapter_compiles.py compiles it against minimal stand-ins
- * of those headers (tests/stubs/) to keep it syntactically and type-wise honest.
+ * of those headers (tests/stubs/) and, on a GPU, runs set_observation / loglikes through it and compares the
+ * log-weights with the oracle (tests/stubs/adapter_run.cpp).
  *
  * What it does is what dbot's KinectImageModelGPU does on the host before its GPU call: compose every
  * particle's delta pose with the integrated (default) pose in double, round R|t to float32, and pass
@@ -44,9 +45,15 @@ public:
                          double tail_weight, double model_sigma, double sigma_factor,
                          double p_occluded_visible, double p_occluded_occluded,
                          double initial_occlusion_prob, double delta_time, int device_id = 0,
-                         double half_life_depth = 1.0, double max_depth = 6.0)
+                         double half_life_depth = 1.0, double max_depth = 6.0,
+                         const std::vector<int>& device_ids = std::vector<int>(), int gather_mode = 0,
+                         bool cull_backfaces = true)
         : n_objects_((int)vertices.size()), handle_(nullptr)
     {
+        /* device_ids: two or more CUDA ordinals shard the particles over those GPUs inside the library (one
+         * process, one sensor object -- what RbSensorBuilder::build() must return); gather_mode 0 = NCCL
+         * all-gather of the log-weights, 1 = stores over NVLink peer memory from the kernel's epilogue.
+         * cull_backfaces = false draws every triangle, as dbot's RigidBodyRenderer does. */
         dbot_b200_config cfg = dbot_b200_config();
         cfg.rows = n_rows;
         cfg.cols = n_cols;
@@ -85,6 +92,11 @@ public:
         cfg.delta_time = delta_time;
         cfg.device_id = device_id;
         cfg.occlusion_mode = 0;
+        cfg.cull_backfaces = cull_backfaces ? 0 : 1;
+        std::vector<int32_t> ids(device_ids.begin(), device_ids.end());
+        cfg.n_devices = (int32_t)ids.size();
+        cfg.device_ids = ids.empty() ? nullptr : ids.data();
+        cfg.gather_mode = gather_mode;
         check(dbot_b200_create(&cfg, &handle_), "create");
         this->default_poses_.resize(n_objects_);
     }

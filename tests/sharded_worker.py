@@ -17,6 +17,39 @@ from dbot_ros_b200 import synth  # noqa: E402
 from dbot_ros_b200.sharded import CrossShardParent, ShardedRbSensor, shard_bounds  # noqa: E402
 
 
+class OracleLocal(oracle_lib.Oracle):
+    """the oracle with the two members of the RbSensor interface a tracker uses beyond loglikes_poses:
+    integrated_poses and compose (what B200KinectImageModel offers on the product side)"""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.integrated_poses = np.zeros((self.n_objects, 6))
+
+    def compose(self, deltas):
+        from dbot_ros_b200.rb_sensor import compose_poses
+
+        return compose_poses(deltas, self.integrated_poses)
+
+    def loglikes(self, deltas, indices, update=False):
+        return self.loglikes_poses(self.compose(deltas), indices, update)
+
+
+def track(sensor, render, n_particles, frames, seed):
+    """a ParticleTracker over `sensor` on a short moving-object sequence -> [frames, 12] estimates"""
+    from dbot_ros_b200.tracker import ParticleTracker, TrackerParameters
+
+    rows, cols = synth.resolution(8)
+    rng = np.random.default_rng(seed)
+    start, step = np.array([0.0, 0.0, 0.8]), np.array([0.002, -0.001, 0.0015])
+    tr = ParticleTracker(sensor, 1, TrackerParameters(evaluation_count=n_particles), seed=seed)
+    tr.initialize([[start[0] + 0.004, start[1] - 0.003, start[2] + 0.004, 0.0, 0.0, 0.0]])
+    est = []
+    for f in range(frames):
+        img = synth.make_frame(render, [(np.eye(3), start + f * step)], rows, cols, rng, occluder=False)
+        est.append(tr.track(img)[0])
+    return np.array(est), tr.resample_count
+
+
 def scenario(n, frames, seed):
     """inputs every rank (and the single-process check) rebuilds identically"""
     rows, cols = synth.resolution(8)
@@ -60,7 +93,7 @@ def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     rows, cols, K, V, T, _, _ = scenario(n, frames, seed)
-    local = oracle_lib.Oracle(rows, cols, K, V, T, synth.default_parameters())
+    local = OracleLocal(rows, cols, K, V, T, synth.default_parameters())
     sensor = ShardedRbSensor(local)
     got = run(sensor, n, frames, world, seed, local.render)
     # with migration disabled a parent on the other rank must be refused, not silently evaluated
@@ -78,10 +111,15 @@ def main():
     migrated = sensor.migrated_slots
     flags = [None] * world
     dist.all_gather_object(flags, refused)
+    # the tracker drives the sharded sensor like any RbSensor: it assigns integrated_poses on it and calls
+    # loglikes(deltas): every rank runs the same filter and must see the track of the unsharded sensor
+    sensor.reset()
+    tracked, resamplings = track(sensor, local.render, 60, 6, seed)
     sensor.reset()
     assert sensor.n_slots == 1
     np.savez(out_path + ".rank%d.npz" % rank, got=got, refused=np.array(flags), lo_hi=np.array(shard_bounds(n, world, rank)),
-             local_slots=local.n_slots, got_global=got_global, migrated=migrated)
+             local_slots=local.n_slots, got_global=got_global, migrated=migrated, tracked=tracked,
+             resamplings=resamplings)
     dist.destroy_process_group()
 
 

@@ -148,6 +148,10 @@ def test_edge_cases():
     poses[1, 0, 9:] = (0.0, 0.0, -0.8)
     poses[2, 0, 9:] = (-0.42, 0.3, 0.8)
     poses[3, 0, 9:] = (0.0, 0.0, 0.05)
+    # far away: the whole object falls on a few pixels, then on a single column / a single pixel
+    poses[4, 0, 9:] = (0.0, 0.0, 12.0)
+    poses[5, 0, 9:] = (0.3, 0.1, 40.0)
+    poses[6, 0, 9:] = (0.0, 0.0, 150.0)
     ia = np.zeros(n, dtype=np.int32)
     ib = np.zeros(n, dtype=np.int32)
     got = sensor.loglikes_poses(poses, ia, False)

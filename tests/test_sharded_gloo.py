@@ -52,6 +52,9 @@ def test_two_ranks_match_one_process(tmp_path, n):
     want = sharded_worker.run(orc, n, frames, world, seed, orc.render)
     orc.reset()
     want_global = sharded_worker.run(orc, n, frames, world, seed + 1, orc.render, global_parents=True)
+    single = sharded_worker.OracleLocal(rows, cols, K, V, T, synth.default_parameters())
+    want_track, want_resamplings = sharded_worker.track(single, single.render, 60, 6, seed)
+    assert np.linalg.norm(want_track[-1, :3] - [0.01, -0.005, 0.8075]) < 0.004     # it does follow the object
     migrated = 0
     for rank in range(world):
         z = np.load(out + ".rank%d.npz" % rank)
@@ -59,6 +62,8 @@ def test_two_ranks_match_one_process(tmp_path, n):
         # parents drawn from all slots: occlusion images migrated between the ranks, results unchanged
         assert np.array_equal(z["got_global"], want_global), "rank %d: cross-rank parents" % rank
         migrated += int(z["migrated"])
+        # a ParticleTracker over the sharded sensor (it sets integrated_poses on it and calls loglikes(deltas))
+        assert np.array_equal(z["tracked"], want_track) and int(z["resamplings"]) == want_resamplings
         assert z["refused"].all()
         lo, hi = z["lo_hi"]
         assert int(z["local_slots"]) == 1  # reset collapsed the local state again

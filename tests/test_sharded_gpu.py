@@ -70,3 +70,54 @@ def test_two_gpu_sharding_is_bit_identical(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_slot_export_import_between_two_handles_on_one_gpu():
+    """the kernels behind cross-GPU resampling (dbot_b200_export_slot_device / import_slot_device) between two
+    handles on ONE GPU, so that a one-GPU box exercises them: a slot exported from A and imported into B is
+    an extra parent slot of B whose children see exactly A's occlusion image; the next update drops it."""
+    import torch
+
+    from dbot_ros_b200 import CameraData, DbotB200Error, ObjectModel, Parameters, RbSensorBuilder, synth
+
+    rows, cols = synth.resolution(4)
+    K = synth.camera_matrix(4)
+    V, T = synth.mesh_set("uvsphere480")
+    n = 24
+    mk = lambda: RbSensorBuilder(ObjectModel(V, T), CameraData(K, rows, cols), Parameters(sample_count=n)).build()  # noqa: E731
+    a, b = mk(), mk()
+    rng = np.random.default_rng(9)
+    gt = synth.ground_truth_poses(1, rng)
+    frames = [synth.make_frame(a.render, gt, rows, cols, rng) for _ in range(3)]
+    pa, pb = synth.particle_poses(gt, n, rng), synth.particle_poses(gt, n, rng, sigma_t=0.02)
+    # same observation / update history on both handles (that is what makes stored images portable),
+    # different particles: their occlusion images differ
+    for s, p in ((a, pa), (b, pb)):
+        s.set_observation(frames[0])
+        s.loglikes_poses(p, np.zeros(n, np.int32), True)
+        s.set_observation(frames[1])
+    assert not np.array_equal(a.occlusion(5), b.occlusion(5))
+    buf = torch.empty(a.slot_floats, dtype=torch.float32, device="cuda")
+    free_before = b.free_slots
+    a.export_slot_device(5, buf.data_ptr())
+    a.synchronize()
+    slot = b.import_slot_device(buf.data_ptr())
+    b.synchronize()
+    assert slot == n and b.n_slots == n + 1 and b.free_slots == free_before - 1
+    assert np.array_equal(b.occlusion(slot), a.occlusion(5))
+    probe = pa[7:8]
+    want = a.loglikes_poses(probe, np.array([5], np.int32), False)
+    got = b.loglikes_poses(probe, np.array([slot], np.int32), False)
+    assert np.array_equal(got, want)
+    # children of the imported slot in an update; afterwards it is gone like any parent
+    idx = np.full(n, slot, np.int32)
+    idx[::2] = np.arange(n, dtype=np.int32)[::2]
+    ia = idx.copy()
+    ia[ia == slot] = 5
+    ra = a.loglikes_poses(pa, ia, True)
+    rb = b.loglikes_poses(pa, idx, True)
+    assert np.array_equal(ra[1::2], rb[1::2])           # the odd particles' parent images were identical
+    assert b.n_slots == n and b.free_slots == free_before
+    assert np.array_equal(a.occlusion(1), b.occlusion(1))
+    with pytest.raises(DbotB200Error):
+        b.export_slot_device(n, buf.data_ptr())
