@@ -12,7 +12,7 @@ particles (ref:source/dbot_ros/object_tracker_ros.hpp:49 -> dbot filter, SURVEY.
           buffers in and host log-weights out -- what the C++ adapter hands over; H2D/D2H inside the
           timed region.  e2e_pinned: the same from page-locked buffers.
   roofline  the fused particle kernel (update).  achieved = the bytes the launch actually has to move
-          (copying children x 8P + covered pixels x 8 per particle) / launch duration from CUDA
+          (copying children x 8 B x touched rows x row pitch + covered pixels x 8 B per particle) / launch duration from CUDA
           events; frac_dram = DRAM bytes ncu counted for the same launch / duration / peak; the
           dense-formulation figure of SURVEY.md 8(d) (8P per particle whether copied or not) is kept
           beside it as dense_equivalent.  `bound` says what ncu shows limits the kernel.
@@ -450,7 +450,11 @@ def main():
     copies = float(np.mean([len(p) - len(np.unique(p)) for p in parents]))
     sample = poses[0][:: max(1, n // 16)][:16]
     n_cov = float(np.mean([np.isfinite(sensor.render(q)).sum() for q in sample]))
-    alg_bytes = copies * 8.0 * P + n * 8.0 * n_cov
+    # a copy moves the rows in which the parent's image can differ from the background (dbot_b200_slot_rows)
+    band = [sensor.slot_rows(sl) for sl in range(0, n, max(1, n // 32))]
+    band_rows = float(np.mean([max(0, b - a + 1) for a, b in band]))
+    pitch = (cols + 7) // 8 * 8
+    alg_bytes = copies * 8.0 * pitch * band_rows + n * 8.0 * n_cov
     dense_bytes = 8.0 * P * n                     # SURVEY.md 8(d), dense formulation: 4P read + 4P written per particle
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
     frac_dram = (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic else None
@@ -465,8 +469,8 @@ def main():
                                   "launch of the same workload)" if traffic else None,
                 "issue_active_pct_ncu": issue_pct,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "algorithmic_bytes": "copying children (%.0f of %d) x 8P + %d covered pixels x 8 B x %d particles"
-                                     % (copies, n, round(n_cov), n),
+                "algorithmic_bytes": "copying children (%.0f of %d) x 8 B x %d px/row x %.0f touched rows + %d covered "
+                                     "pixels x 8 B x %d particles" % (copies, n, pitch, band_rows, round(n_cov), n),
                 "dense_equivalent": {"bytes_per_launch": dense_bytes, "GBps": dense_bytes / (avg_ms * 1e-3) / 1e9,
                                      "frac": dense_bytes / (avg_ms * 1e-3) / 1e9 / peak,
                                      "note": "8P per particle whether copied or not (SURVEY.md 8d); not a DRAM rate"},

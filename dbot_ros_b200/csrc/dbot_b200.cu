@@ -96,6 +96,10 @@ struct dbot_kparams
     const int4* plan;       /* update: per particle { source slot, destination slot, parent, 0 } (physical) */
     const int32_t* order;   /* update: processing order, copying children before adopting ones */
     int32_t* pending;       /* update: per parent, copies of its image still to be read */
+    int2* slot_rows;        /* [2 * max_particles] per PHYSICAL slot: first and last image row that may differ from
+                               the background value (empty: first > last).  Every stored image equals the
+                               background outside these rows, so a copy moves only the parent's rows. */
+    float background;       /* stored value of a never-updated pixel (lazy encoding: constant between rebases) */
     size_t slot_stride;     /* rows*pitch */
     float post_b, post_inv_a; /* update: the posterior o is stored as (o - post_b) * post_inv_a */
     const float* poses;     /* [n][n_obj][12] */
@@ -159,6 +163,8 @@ struct dbot_b200_sensor
     int32_t* d_free;        /* stack of unused physical slots + its height */
     int32_t* d_free_count;
     int32_t *d_cnt, *d_last, *d_pending, *d_order;
+    int2* d_slot_rows;      /* touched row range of every physical slot */
+    double background;      /* stored value of untouched pixels */
     int4* d_plan;
     float* d_poses;
     int32_t* d_indices;
@@ -399,7 +405,7 @@ extern "C" int dbot_b200_destroy(dbot_b200_sensor* s)
     cudaFree(s->d_mesh); cudaFree(s->d_chunks); cudaFree(s->d_obs); cudaFree(s->d_tab);
     cudaFree(s->d_pool); cudaFree(s->d_loc[0]); cudaFree(s->d_loc[1]); cudaFree(s->d_free);
     cudaFree(s->d_free_count); cudaFree(s->d_cnt); cudaFree(s->d_last); cudaFree(s->d_pending);
-    cudaFree(s->d_order); cudaFree(s->d_plan); cudaFree(s->d_poses); cudaFree(s->d_indices);
+    cudaFree(s->d_order); cudaFree(s->d_plan); cudaFree(s->d_slot_rows); cudaFree(s->d_poses); cudaFree(s->d_indices);
     cudaFree(s->d_out); cudaFree(s->d_depth); cudaFree(s->d_err);
     cudaFreeHost(s->h_poses); cudaFreeHost(s->h_indices); cudaFreeHost(s->h_out);
     cudaFreeHost(s->h_obs); cudaFreeHost(s->h_depth); cudaFreeHost(s->h_err);
@@ -522,6 +528,7 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     CUDA_TRY(cudaMalloc(&s->d_last, 2 * np * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&s->d_pending, 2 * np * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&s->d_order, np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_slot_rows, 2 * np * sizeof(int2)));
     CUDA_TRY(cudaMalloc(&s->d_plan, np * sizeof(int4)));
     CUDA_TRY(cudaMalloc(&s->d_poses, np * 12 * kp.n_obj * sizeof(float)));
     CUDA_TRY(cudaMalloc(&s->d_indices, np * sizeof(int32_t)));
@@ -601,7 +608,8 @@ static void prof_end(dbot_b200_sensor* s, int which)
 
 /* RbSensor::reset: one logical slot (physical slot 0) at initial_occlusion_prob,
  * every other physical slot free */
-__global__ void dbot_reset_slots_kernel(int32_t* loc, int32_t* free_stack, int32_t* free_count, int n_phys)
+__global__ void dbot_reset_slots_kernel(int32_t* loc, int32_t* free_stack, int32_t* free_count, int2* slot_rows,
+                                        int n_phys, int rows)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0)
@@ -610,6 +618,7 @@ __global__ void dbot_reset_slots_kernel(int32_t* loc, int32_t* free_stack, int32
         *free_count = n_phys - 1;
     }
     if (i < n_phys - 1) free_stack[i] = n_phys - 1 - i; /* top of the stack = slot 1 */
+    if (i < n_phys) slot_rows[i] = make_int2(rows, -1);  /* every slot holds the background everywhere */
 }
 
 __global__ void dbot_free_all_slots_kernel(int32_t* free_stack, int32_t* free_count, int n_phys)
@@ -634,10 +643,13 @@ extern "C" int dbot_b200_reset(dbot_b200_sensor* s)
     s->A = 1.0;
     s->B = 0.0;
     const int n_phys = 2 * s->cfg.max_particles;
-    dbot_fill_kernel<<<64, 256, 0, s->stream>>>(s->d_pool, s->kp.slot_stride,
-                                                (float)s->cfg.initial_occlusion_prob);
-    dbot_reset_slots_kernel<<<(n_phys + 255) / 256, 256, 0, s->stream>>>(s->d_loc[0], s->d_free,
-                                                                         s->d_free_count, n_phys);
+    /* EVERY physical slot starts as the background image: the copies of an update rely on a recycled slot
+     * holding the background outside its recorded rows */
+    s->background = s->cfg.initial_occlusion_prob;
+    dbot_fill_kernel<<<s->num_sms * 8, 256, 0, s->stream>>>(s->d_pool, (size_t)n_phys * s->kp.slot_stride,
+                                                            (float)s->background);
+    dbot_reset_slots_kernel<<<(n_phys + 255) / 256, 256, 0, s->stream>>>(s->d_loc[0], s->d_free, s->d_free_count,
+                                                                         s->d_slot_rows, n_phys, s->kp.rows);
     s->launches += 2;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -733,10 +745,12 @@ static int launch_particles(dbot_b200_sensor* s, const float* d_poses, int32_t* 
     if (update && A < DBOT_REBASE_BELOW)
     {
         /* fold the accumulated map into the stored values before it leaves float range */
-        dbot_rebase_kernel<<<dim3(32, std::min(s->n_slots, 4096)), 256, 0, s->stream>>>(
-            s->d_pool, s->d_loc[s->cur], s->n_slots, s->kp.slot_stride, (float)s->A, (float)s->B);
+        /* every physical slot, free ones included: they must keep holding the (new) background value */
+        dbot_rebase_kernel<<<s->num_sms * 8, 256, 0, s->stream>>>(
+            s->d_pool, (size_t)2 * s->cfg.max_particles * s->kp.slot_stride, (float)s->A, (float)s->B);
         s->launches++;
         CUDA_TRY(cudaGetLastError());
+        s->background = (double)fmaf((float)s->A, (float)s->background, (float)s->B);
         s->A = 1.0;
         s->B = 0.0;
         state_affine_now(s, &A, &B);
@@ -750,6 +764,8 @@ static int launch_particles(dbot_b200_sensor* s, const float* d_poses, int32_t* 
     kp.plan = s->d_plan;
     kp.order = s->d_order;
     kp.pending = s->d_pending;
+    kp.slot_rows = s->d_slot_rows;
+    kp.background = (float)s->background;
     kp.poses = d_poses;
     kp.indices = d_indices;
     kp.out = d_out;
@@ -981,7 +997,7 @@ __global__ void dbot_export_slot_kernel(const float* __restrict__ pool, const in
         out[i] = src[i];
 }
 __global__ void dbot_import_pop_kernel(int32_t* loc, int32_t* free_stack, int32_t* free_count, int slot,
-                                       int* err_flag)
+                                       int* err_flag, int2* slot_rows, int rows)
 {
     const int f = *free_count;
     if (f <= 0)
@@ -991,6 +1007,7 @@ __global__ void dbot_import_pop_kernel(int32_t* loc, int32_t* free_stack, int32_
         return;
     }
     loc[slot] = free_stack[f - 1];
+    slot_rows[free_stack[f - 1]] = make_int2(0, rows - 1); /* an imported image may differ from the background anywhere */
     *free_count = f - 1;
 }
 __global__ void dbot_import_copy_kernel(float* __restrict__ pool, const int32_t* __restrict__ loc, int slot,
@@ -1027,12 +1044,36 @@ extern "C" int dbot_b200_import_slot_device(dbot_b200_sensor* s, const float* d_
         return fail(-2, "import_slot: %d slots are live, the pool holds %d", s->n_slots, 2 * s->cfg.max_particles);
     CUDA_TRY(cudaSetDevice(s->device));
     const int slot = s->n_slots;
-    dbot_import_pop_kernel<<<1, 1, 0, s->stream>>>(s->d_loc[s->cur], s->d_free, s->d_free_count, slot, s->d_err);
+    dbot_import_pop_kernel<<<1, 1, 0, s->stream>>>(s->d_loc[s->cur], s->d_free, s->d_free_count, slot, s->d_err,
+                                                   s->d_slot_rows, s->kp.rows);
     dbot_import_copy_kernel<<<64, 256, 0, s->stream>>>(s->d_pool, s->d_loc[s->cur], slot, s->kp.slot_stride, d_src);
     s->launches += 2;
     CUDA_TRY(cudaGetLastError());
     s->n_slots = slot + 1;
     *out_slot = slot;
+    return 0;
+}
+
+/* first / last image row of a slot that may differ from the background (first > last: none) */
+extern "C" int dbot_b200_slot_rows(dbot_b200_sensor* s, int32_t slot, int32_t* out_first, int32_t* out_last)
+{
+    if (!s || !out_first || !out_last) return fail(-1, "slot_rows: null argument");
+    if (s->multi)
+    {
+        if (slot < 0 || slot >= multi_n_slots(s)) return fail(-7, "slot_rows: slot %d of %d", slot, multi_n_slots(s));
+        int32_t local = 0;
+        dbot_b200_sensor* owner = multi_owner(s, slot, &local);
+        return dbot_b200_slot_rows(owner, local, out_first, out_last);
+    }
+    if (slot < 0 || slot >= s->n_slots) return fail(-7, "slot_rows: slot %d of %d", slot, s->n_slots);
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    int32_t phys = 0;
+    int2 r;
+    CUDA_TRY(cudaMemcpy(&phys, s->d_loc[s->cur] + slot, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&r, s->d_slot_rows + phys, sizeof(int2), cudaMemcpyDeviceToHost));
+    *out_first = r.x;
+    *out_last = r.y;
     return 0;
 }
 

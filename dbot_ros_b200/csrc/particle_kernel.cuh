@@ -297,28 +297,53 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
     {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DBOT_STREAM_REGS));
         const int sl = tid - DBOT_CT;
-        const int n8 = (int)(p.slot_stride >> 3);
-        /* The loads below keep only DBOT_STREAM_UNROLL x 32 B per thread in flight -- far too
+        const size_t row8 = (size_t)p.pitch >> 3; /* 256-bit words per image row */
+        /* Only the rows in which the parent's image can differ from the background are copied
+         * (dbot_kparams::slot_rows): every image is the background value outside its recorded rows, the
+         * recycled destination slot included -- whose own old rows are first put back to the background
+         * where the parent's rows do not cover them.  A tracked object touches a band of the image, not all
+         * of it; when it has wandered over every row this is the dense copy again.
+         * The loads below keep only DBOT_STREAM_UNROLL x 32 B per thread in flight -- far too
          * little for HBM latency.  One lane therefore runs a TMA prefetch (cp.async.bulk.prefetch.L2)
          * DBOT_PREFETCH_AHEAD chunks ahead of the loop, across particle boundaries, so that the
          * loads hit L2. */
         constexpr int CHUNK8 = DBOT_ST * DBOT_STREAM_UNROLL;       /* 256-bit words per chunk */
-        const int n_chunks = (n8 + CHUNK8 - 1) / CHUNK8;
-        auto next_copy = [&](int k) { /* source of the next copying child of this CTA */
+        auto rows_of = [&](int phys, size_t& first8, int& n8) { /* word range holding the slot's recorded rows */
+            const int2 r = p.slot_rows[phys];
+            first8 = r.x <= r.y ? (size_t)r.x * row8 : 0;
+            n8 = r.x <= r.y ? (int)((size_t)(r.y - r.x + 1) * row8) : 0;
+            return r;
+        };
+        auto next_copy = [&](int k, int& n8_next) -> const float* { /* source range of this CTA's next copy */
             for (k += gridDim.x; k < p.n; k += gridDim.x)
             {
                 const int4 pl = p.plan[p.order[k]];
-                if (pl.x >= 0 && pl.x != pl.y) return pl.x;
+                if (pl.x >= 0 && pl.x != pl.y)
+                {
+                    size_t f8;
+                    rows_of(pl.x, f8, n8_next);
+                    return p.pool + (size_t)pl.x * p.slot_stride + (f8 << 3);
+                }
             }
-            return -1;
+            n8_next = 0;
+            return nullptr;
         };
-        auto prefetch_chunk = [&](const float* src, int c) {
+        auto prefetch_chunk = [&](const float* src, int n8, int c) {
             const int q0 = c * CHUNK8;
             const int nq = min(CHUNK8, n8 - q0);
             if (nq > 0)
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + ((size_t)q0 << 3)),
                              "r"(nq * 32)
                              : "memory");
+        };
+        auto fill_rows = [&](float* slot, int ra, int rb) { /* rows [ra, rb] of a slot <- background */
+            if (ra > rb) return;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = p.background;
+            float* dst = slot + (((size_t)ra * row8) << 3);
+            const int n8 = (int)((size_t)(rb - ra + 1) * row8);
+            for (int q = sl; q < n8; q += DBOT_ST) stg256_stream(dst + ((size_t)q << 3), v);
         };
         bool first = true;
         int done = 0;
@@ -328,29 +353,40 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
             if (pl.x < 0) continue;
             if (pl.x != pl.y)
             {
-                const float* in = p.pool + (size_t)pl.x * p.slot_stride;
-                float* out = p.pool + (size_t)pl.y * p.slot_stride;
+                size_t f8;
+                int n8;
+                const int2 pr = rows_of(pl.x, f8, n8);
+                const int2 dr = p.slot_rows[pl.y];
+                const float* in = p.pool + (size_t)pl.x * p.slot_stride + (f8 << 3);
+                float* slot = p.pool + (size_t)pl.y * p.slot_stride;
+                float* out = slot + (f8 << 3);
+                const int n_chunks = (n8 + CHUNK8 - 1) / CHUNK8;
                 const float* in_next = nullptr;
+                int n8_next = 0;
                 if (sl == 0)
                 {
-                    const int snext = next_copy(k);
-                    if (snext >= 0) in_next = p.pool + (size_t)snext * p.slot_stride;
+                    in_next = next_copy(k, n8_next);
                     if (first)
-                        for (int c = 0; c < DBOT_PREFETCH_AHEAD; ++c) prefetch_chunk(in, c);
+                        for (int c = 0; c < DBOT_PREFETCH_AHEAD; ++c) prefetch_chunk(in, n8, c);
                 }
                 first = false;
-#ifdef DBOT_DBG_NO_STREAM
-                if (p.n == 0x7654321)
-#endif
+                /* what the recycled slot held outside the parent's rows */
+                if (pr.x <= pr.y)
+                {
+                    fill_rows(slot, dr.x, min(dr.y, pr.x - 1));
+                    fill_rows(slot, max(dr.x, pr.y + 1), dr.y);
+                }
+                else
+                    fill_rows(slot, dr.x, dr.y);
                 for (int c = 0; c < n_chunks; ++c)
                 {
                     if (sl == 0)
                     {
                         const int cp = c + DBOT_PREFETCH_AHEAD;
                         if (cp < n_chunks)
-                            prefetch_chunk(in, cp);
+                            prefetch_chunk(in, n8, cp);
                         else if (in_next)
-                            prefetch_chunk(in_next, cp - n_chunks);
+                            prefetch_chunk(in_next, n8_next, cp - n_chunks);
                     }
                     const int base = c * CHUNK8 + sl;
                     float v[DBOT_STREAM_UNROLL][8];
@@ -371,6 +407,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                 stream_sync();   /* ... and so is everybody else's */
                 if (sl == 0)
                 {
+                    p.slot_rows[pl.y] = pr;         /* the child's image differs from the background where the parent's does */
                     atomicSub(p.pending + pl.z, 1); /* one reader of the parent's slot less */
                     ++done;
                     asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(&s_copied)), "r"(done)
@@ -737,7 +774,15 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                            MODE, i, tl[1] - tl[0], tl[2] - tl[1], tl[3] - tl[2], tl[4] - tl[3], tl[5] - tl[4],
                            tl[6] - tl[5], tl[6] - tl[0]);
 #endif
-                if (MODE == DBOT_MODE_UPDATE) p.indices[i] = i;
+                if (MODE == DBOT_MODE_UPDATE)
+                {
+                    p.indices[i] = i;
+                    if (have_window) /* posteriors were written inside rows [r0, r1] of the slot */
+                    {
+                        const int2 cur = p.slot_rows[pl.y];
+                        p.slot_rows[pl.y] = make_int2(min(cur.x, r0), max(cur.y, r1));
+                    }
+                }
             }
         }
     }

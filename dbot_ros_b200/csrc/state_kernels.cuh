@@ -42,18 +42,13 @@ __global__ void dbot_fill_kernel(float* __restrict__ dst, size_t n, float v)
     for (; i < n; i += stride) dst[i] = v;
 }
 
-/* rebase of the lazily propagated state: stored <- A * stored + B in every live slot (rare: once the
- * accumulated factor A has shrunk to 2^-60, i.e. after roughly 80 s of tracking) */
-__global__ void dbot_rebase_kernel(float* __restrict__ pool, const int32_t* __restrict__ loc, int n_slots,
-                                   size_t slot_stride, float A, float B)
+/* rebase of the lazily propagated state: stored <- A * stored + B in every physical slot, the unused ones
+ * included (they keep holding the background value, see dbot_kparams::slot_rows); rare: once the
+ * accumulated factor A has shrunk to 2^-60, i.e. after roughly 80 s of tracking */
+__global__ void dbot_rebase_kernel(float* __restrict__ pool, size_t n, float A, float B)
 {
-    for (int sidx = blockIdx.y; sidx < n_slots; sidx += gridDim.y)
-    {
-        float* dst = pool + (size_t)loc[sidx] * slot_stride;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < slot_stride;
-             i += (size_t)gridDim.x * blockDim.x)
-            dst[i] = __fmaf_rn(A, dst[i], B);
-    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        pool[i] = __fmaf_rn(A, pool[i], B);
 }
 
 /* ------------------------------------------------------------------------------------------ */

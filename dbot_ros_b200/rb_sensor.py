@@ -333,6 +333,13 @@ class B200KinectImageModel(RbSensor):
         """+1 / -1: back faces of this object are skipped (mesh proven closed); 0: all triangles drawn"""
         return self._lib.dbot_b200_cull_sign(self._h, int(obj))
 
+    def slot_rows(self, slot):
+        """(first, last) image row in which the slot's stored image may differ from the background; first > last
+        when it is the background everywhere"""
+        a, b = C.c_int32(), C.c_int32()
+        abi.check(self._lib, self._lib.dbot_b200_slot_rows(self._h, int(slot), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     @property
     def free_slots(self):
         return self._lib.dbot_b200_free_slot_count(self._h)

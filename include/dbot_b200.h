@@ -61,7 +61,8 @@ typedef struct
     int32_t device_id;   /* CUDA device ordinal of a single-device handle (n_devices <= 1 and no device_ids) */
     int32_t occlusion_mode; /* 0 = dense: one full-frame fp32 occlusion image per particle with the
                                semantics of dbot's GPU evaluator (whole image propagated on every
-                               update).  Other values are reserved. */
+                               update; the propagation is kept as two numbers, and an update moves only the
+                               image rows an ancestor has ever written).  Other values are reserved. */
     int32_t cull_backfaces; /* 0 = triangles facing away from the camera are skipped for every object whose
                                mesh is proven closed and consistently oriented (dbot_b200_cull_sign != 0;
                                the nearest surface of such a mesh is always camera-facing, so the rendered
@@ -168,6 +169,9 @@ int dbot_b200_n_slots(dbot_b200_sensor* s);
  * triangles that are drawn, 0 = all triangles are drawn */
 int dbot_b200_cull_sign(dbot_b200_sensor* s, int32_t object);
 double dbot_b200_observation_time(dbot_b200_sensor* s);
+/* first and last image row in which a slot's stored image may differ from the background value (first > last:
+ * nowhere).  An update copies only these rows of a parent to a child that does not adopt its slot. */
+int dbot_b200_slot_rows(dbot_b200_sensor* s, int32_t slot, int32_t* out_first, int32_t* out_last);
 /* physical occlusion slots not in use (pool of 2*max_particles; n_slots + free == pool size) */
 int dbot_b200_free_slot_count(dbot_b200_sensor* s);
 /* occlusion probability image of one slot as of the current observation time, rows*cols floats */

@@ -404,3 +404,42 @@ def test_maximum_sizes_and_ragged_inputs():
     ia, ib = np.zeros(1, np.int32), np.zeros(1, np.int32)
     assert rel_err(sensor.loglikes_poses(poses, ia, True), orc.loglikes_poses(poses, ib, True)) < REL_TOL
     assert np.max(np.abs(sensor.occlusion(0) - orc.occlusion(0))) < OCC_TOL
+
+
+def test_updates_copy_only_touched_rows_and_images_stay_exact():
+    """An update copies only the rows of the parent's image that an ancestor has ever written
+    (dbot_b200_slot_rows); everything else must already be the background in the recycled destination slot.
+    Two groups of particles track objects at different heights; resampling moves children between the groups,
+    so slots recycled from the tall band are reused under parents with the short band and the other way round.
+    Every occlusion image is compared with the oracle in full, frame after frame."""
+    n = 40
+    sensor, orc, rows, cols, _ = make_pair("ico80", 4, n)
+    rng = np.random.default_rng(21)
+    assert sensor.slot_rows(0) == (rows, -1)                      # reset: background everywhere
+    top = [(np.eye(3), np.array([0.0, -0.12, 0.8]))]
+    low = [(np.eye(3), np.array([0.05, 0.14, 0.9]))]
+    idx = np.zeros(n, dtype=np.int32)
+    for f in range(6):
+        frame = synth.make_frame(orc.render, top if f % 2 == 0 else low, rows, cols, rng)
+        poses = np.concatenate([synth.particle_poses(top, n // 2, rng), synth.particle_poses(low, n - n // 2, rng)])
+        if f == 3:
+            poses[:] = synth.particle_poses(top, n, rng)         # everybody jumps to the upper object
+        if f > 0:
+            idx = rng.integers(0, n, size=n).astype(np.int32)     # parents from either group
+            if f == 4:
+                idx = np.sort(rng.choice(np.arange(n // 2, n), n)).astype(np.int32)   # only lower-group parents
+        for s in (sensor, orc):
+            s.set_observation(frame)
+        ia, ib = idx.copy(), idx.copy()
+        got = sensor.loglikes_poses(poses, ia, True)
+        want = orc.loglikes_poses(poses, ib, True)
+        assert rel_err(got, want) < REL_TOL
+        for slot in range(n):
+            assert np.max(np.abs(sensor.occlusion(slot) - orc.occlusion(slot))) < OCC_TOL, (f, slot)
+        a, b = sensor.slot_rows(0)
+        assert 0 <= a <= b < rows
+    # the bands stayed bands: the upper object never touched the bottom rows and vice versa
+    spans = [sensor.slot_rows(s) for s in range(n)]
+    assert max(b - a + 1 for a, b in spans) < rows
+    sensor.reset()
+    assert sensor.slot_rows(0) == (rows, -1)
