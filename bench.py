@@ -529,7 +529,10 @@ def main():
         # multi-GPU behind the C-ABI (one process, one handle): measured by rank 0 alone while the other ranks
         # wait with idle GPUs.  Weak-scaled config 2 (comparable with this line's value) and, on 8 GPUs or with
         # DBOT_BENCH_CONFIG4=1, BASELINE config 4 at its stated size (8 x 10 000 = 80 000 particles).
+        # (the others wait on the rendezvous store, i.e. on the CPU: a NCCL barrier would keep a kernel spinning
+        # on their GPUs and the two processes would time-slice them)
         sync_all()
+        store = dist.distributed_c10d._get_default_store()
         if rank == 0:
             sp = {}
             try:
@@ -544,10 +547,14 @@ def main():
             except Exception as e:  # the bench line does not depend on it
                 sp["error"] = str(e)
             line["single_process"] = sp
+            store.set("dbot_single_process_done", "1")
+        else:
+            store.wait(["dbot_single_process_done"])
         dist.barrier()
     if rank == 0:
         emit(line)
     if world > 1:
+        sharded.close()
         dist.destroy_process_group()
 
 

@@ -18,7 +18,9 @@ delta pose with the integrated (default) pose and hand R|t per object to the dev
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -209,6 +211,26 @@ class RbSensor:
         raise NotImplementedError
 
 
+# Handles still open when the interpreter exits are closed from a Python atexit hook, i.e. BEFORE the CUDA
+# runtime's own exit handler runs: a __del__ that reaches cudaFree / cudaStreamDestroy after the runtime has
+# torn itself down (module-level sensors are finalised that late) crashes the process on its way out.
+_LIVE_SENSORS = weakref.WeakSet()
+_LIVE_FILTERS = weakref.WeakSet()     # device-resident filters hold their sensor's stream: closed first
+_LIVE_WRAPPERS = weakref.WeakSet()    # sharded wrappers hold torch buffers tied to a sensor's stream: closed before it
+
+
+def _close_all_at_exit():
+    for group in (_LIVE_WRAPPERS, _LIVE_FILTERS, _LIVE_SENSORS):
+        for obj in list(group):
+            try:
+                obj.close()
+            except Exception:
+                pass
+
+
+atexit.register(_close_all_at_exit)
+
+
 class B200KinectImageModel(RbSensor):
     """The sensor RbSensorBuilder.build() returns when use_gpu is true: stands where dbot's
     KinectImageModelGPU stood, backed by libdbot_b200.so."""
@@ -233,6 +255,7 @@ class B200KinectImageModel(RbSensor):
             cull_backfaces=0 if getattr(params, "cull_backfaces", True) else 1,
             device_ids=device_ids, gather_mode=gather_mode)
         abi.check(self._lib, self._lib.dbot_b200_create(C.byref(cfg), C.byref(self._h)))
+        _LIVE_SENSORS.add(self)
         # RbSensor::default_poses_ -- one PoseVector (position, euler vector) per object
         self._default_poses = np.zeros((self.n_objects, 6))
 

@@ -75,6 +75,26 @@ class ShardedRbSensor(RbSensor):
         self._imported_keys = [set() for _ in range(self.world)]
         self._imported_local = {}
         self.migrated_slots = 0   # slots this rank has received so far (statistics)
+        from .rb_sensor import _LIVE_WRAPPERS
+
+        _LIVE_WRAPPERS.add(self)
+
+    def close(self):
+        """Release the torch buffers that were used on the local sensor's stream while that stream still exists:
+        page-locked host tensors remember the streams they were copied on, and releasing them after the library
+        has destroyed its stream aborts the process.  Called from the package's atexit hook as well."""
+        if self._buf is not None and self.device.type == "cuda":
+            import torch
+
+            try:
+                self.local.synchronize()
+            except Exception:
+                pass
+            torch.cuda.synchronize(self.device)
+        for name in ("_h_poses", "_h_idx", "_d_poses", "_d_idx", "_d_out", "_buf", "_h_all", "_ext", "_send_host",
+                     "_recv_host", "_send"):
+            if hasattr(self, name):
+                setattr(self, name, None)
 
     # -- RbSensor ---------------------------------------------------------------------------
     def reset(self):

@@ -311,6 +311,9 @@ class DeviceParticleTracker:
         self._lib = sensor._lib
         self._h = C.c_void_p()
         abi.check(self._lib, self._lib.dbot_b200_filter_create(sensor._h, C.byref(cfg), C.byref(self._h)))
+        from .rb_sensor import _LIVE_FILTERS
+
+        _LIVE_FILTERS.add(self)
         self.resample_count = 0
 
     def initialize(self, initial_poses):

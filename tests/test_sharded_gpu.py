@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 WORKER = r'''
-import os, sys
+import faulthandler, os, sys
+faulthandler.enable()
 import numpy as np
 import torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(sys.argv[0]))) if False else os.environ["DBOT_ROOT"])
@@ -42,6 +43,7 @@ for f in range(5):
     elif f > 2:          # global resampling: occlusion images migrate over NVLink
         idx = np.sort(rng.integers(0, n, size=n)).astype(np.int32)
     i1, i2 = idx.copy(), idx.copy()
+    print("rank", rank, "frame", f, "migrated so far", sharded.migrated_slots, file=sys.stderr, flush=True)
     sharded.set_observation(frame)
     got = sharded.loglikes_poses(poses, i1, True)
     if rank == 0:
@@ -53,6 +55,8 @@ dist.all_reduce(moved)
 ok = ok and int(moved.item()) > 0
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+print("rank %d bit-identical to one GPU: %s slots migrated (all ranks): %d\n" % (rank, bool(ok), int(moved.item())), end="", flush=True)
+sharded.close()
 dist.destroy_process_group()
 sys.exit(0 if int(flag.item()) == 1 else 3)
 '''
@@ -70,6 +74,8 @@ def test_two_gpu_sharding_is_bit_identical(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "bit-identical to one GPU: True" in r.stdout, r.stdout[-2000:]
+    print(r.stdout[-600:])
 
 
 def test_slot_export_import_between_two_handles_on_one_gpu():
