@@ -702,8 +702,14 @@ extern "C" int dbot_b200_set_observation(dbot_b200_sensor* s, const float* depth
      * running -- every later call on this handle is ordered behind them on the same stream, and the
      * staging buffer is not touched again before they are done */
     if (s->obs_in_flight) CUDA_TRY(cudaEventSynchronize(s->ev_obs));
-    memcpy(s->h_obs, depth_m, bytes);
-    CUDA_TRY(cudaMemcpyAsync(s->d_obs, s->h_obs, bytes, cudaMemcpyHostToDevice, s->stream));
+    /* in four pieces, so that the copy engine moves one piece while the host stages the next */
+    const size_t total = (size_t)s->kp.rows * s->kp.cols;
+    for (int piece = 0; piece < 4; ++piece)
+    {
+        const size_t a = total * piece / 4, b = total * (piece + 1) / 4;
+        memcpy(s->h_obs + a, depth_m + a, (b - a) * sizeof(float));
+        CUDA_TRY(cudaMemcpyAsync(s->d_obs + a, s->h_obs + a, (b - a) * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    }
     CUDA_TRY(cudaEventRecord(s->ev_obs, s->stream));
     s->obs_in_flight = 1;
     return launch_observation(s, s->d_obs);

@@ -27,6 +27,8 @@
 #pragma once
 #include <dlfcn.h>
 
+#include <thread>
+
 /* the handful of NCCL declarations this file needs (bound with dlsym; nccl.h is not required to build) */
 typedef struct ncclComm* dbot_nccl_comm;
 typedef int (*pfn_ncclCommInitAll)(dbot_nccl_comm*, int, const int*);
@@ -378,30 +380,45 @@ static int multi_loglikes(dbot_b200_sensor* s, const float* poses, int32_t* indi
     if (rc) return rc;
     const int32_t* local = m->local_idx->data();
     const size_t pose_stride = (size_t)12 * s->kp.n_obj;
-    int cnt = 0;
-    for (int g = 0; g < G; ++g)
-    {
-        int lo, hi;
-        multi_bounds(n, G, g, &lo, &hi, &cnt);
+    int cnt = (n + G - 1) / G;
+    /* one host thread per shard stages that shard's slice and enqueues its copies and kernels: done one
+     * after the other from a single thread, the last GPU of eight would start half a millisecond late */
+    int shard_rc[DBOT_B200_MAX_DEVICES] = {0};
+    std::string shard_err[DBOT_B200_MAX_DEVICES];
+    auto enqueue_shard = [&](int g) {
+        int lo, hi, c_unused;
+        multi_bounds(n, G, g, &lo, &hi, &c_unused);
         dbot_b200_sensor* c = m->child[g];
-        CUDA_TRY(cudaSetDevice(m->dev[g]));
-        if (hi == lo)
-        {
-            if (update && (rc = empty_update(c))) return rc;
-            continue;
-        }
-        /* the shard's kernel writes its log-weights to its own d_out and, fused mode, into every device's
-         * gathered vector at g * cnt + i */
-        c->kp.n_peers = 0;
-        if (m->gather_mode == 1)
-        {
-            c->kp.n_peers = G;
-            c->kp.out_offset = g * cnt;
-            for (int h = 0; h < G; ++h) c->kp.peer_out[h] = m->d_all[h];
-        }
-        rc = loglikes_enqueue(c, poses + (size_t)lo * pose_stride, local + lo, hi - lo, update);
-        if (rc) return rc;
+        auto body = [&]() -> int {
+            CUDA_TRY(cudaSetDevice(m->dev[g]));
+            if (hi == lo) return update ? empty_update(c) : 0;
+            /* the shard's kernel writes its log-weights to its own d_out and, fused mode, into every device's
+             * gathered vector at g * cnt + i */
+            c->kp.n_peers = 0;
+            if (m->gather_mode == 1)
+            {
+                c->kp.n_peers = G;
+                c->kp.out_offset = g * cnt;
+                for (int h = 0; h < G; ++h) c->kp.peer_out[h] = m->d_all[h];
+            }
+            return loglikes_enqueue(c, poses + (size_t)lo * pose_stride, local + lo, hi - lo, update);
+        };
+        shard_rc[g] = body();
+        if (shard_rc[g]) shard_err[g] = g_last_error; /* thread-local: carried back to the caller's thread */
+    };
+    {
+        std::thread workers[DBOT_B200_MAX_DEVICES];
+        for (int g = 1; g < G; ++g) workers[g] = std::thread(enqueue_shard, g);
+        enqueue_shard(0);
+        for (int g = 1; g < G; ++g) workers[g].join();
     }
+    for (int g = 0; g < G; ++g)
+        if (shard_rc[g])
+        {
+            g_last_error = shard_err[g];
+            if (update) s->poisoned = 1; /* other shards may already have committed this update */
+            return shard_rc[g];
+        }
     if (m->gather_mode == 0)
     {
         int nrc = m->GroupStart();

@@ -40,7 +40,7 @@ struct dbot_raster_smem
     uint16_t* list;       /* [ntri] survivors from the front, tall / wide triangles from the back */
     uint32_t* mask;       /* this warp's first-row mask, 32 words */
     uint32_t* wt;         /* inverse-depth tile */
-    int* counters;        /* [0] survivors, [1] tall + wide, [2] next batch */
+    int* counters;        /* [0] survivors | tall + wide << 16, [2] next batch */
 };
 
 __device__ __forceinline__ dbot_vertex dbot_load_vertex(const dbot_raster_smem& S, int i)
@@ -71,19 +71,17 @@ __device__ __forceinline__ void dbot_raster_prepass(const dbot_raster_smem& S, i
         }
         const unsigned m_front = __ballot_sync(DBOT_FULL, kind == DBOT_TRI_SPANS);
         const unsigned m_back = __ballot_sync(DBOT_FULL, kind >= DBOT_TRI_TALL);
-        int b_front = 0, b_back = 0;
-        if (lane == 0)
-        {
-            if (m_front) b_front = atomicAdd(&S.counters[0], __popc(m_front));
-            if (m_back) b_back = atomicAdd(&S.counters[1], __popc(m_back));
-        }
+        /* one shared atomic per warp and step: survivors in the low half of the counter word, tall + wide
+         * triangles (rare) in the high half */
+        int base_fb = 0;
+        if (lane == 0 && (m_front | m_back))
+            base_fb = atomicAdd(&S.counters[0], __popc(m_front) | (__popc(m_back) << 16));
         __syncwarp();
-        b_front = __shfl_sync(DBOT_FULL, b_front, 0);
-        b_back = __shfl_sync(DBOT_FULL, b_back, 0);
+        base_fb = __shfl_sync(DBOT_FULL, base_fb, 0);
         if (kind == DBOT_TRI_SPANS)
-            S.list[b_front + __popc(m_front & lt)] = (uint16_t)t;
+            S.list[(base_fb & 0xffff) + __popc(m_front & lt)] = (uint16_t)t;
         else if (kind >= DBOT_TRI_TALL)
-            S.list[ntri - 1 - (b_back + __popc(m_back & lt))] =
+            S.list[ntri - 1 - ((base_fb >> 16) + __popc(m_back & lt))] =
                 (uint16_t)(t | (kind == DBOT_TRI_WIDE ? DBOT_LIST_WIDE : 0u));
     }
 }
@@ -145,7 +143,7 @@ __device__ __forceinline__ void dbot_raster_sweep(const dbot_raster_smem& S, int
     /* per-lane dummy words for finished spans: the warp's first-row mask, which is dead while the units run
      * and rewritten at the start of the next batch (one word per lane: no bank conflict) */
     const uint32_t dummy_s = smem_u32(S.mask + lane);
-    const int n_front = S.counters[0], n_back = S.counters[1];
+    const int n_front = S.counters[0] & 0xffff, n_back = S.counters[0] >> 16;
     const int front_batches = (n_front + 31) >> 5;
     const unsigned le = 0xffffffffu >> (31 - lane);
     for (;;)
@@ -694,29 +692,36 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                     const int npx = (rb1 - rb0 + 1) * ww;
                     const uint32_t inv_ww = ww > 1 ? 0xffffffffu / (uint32_t)ww + 1u : 0u;
                     const uint32_t g0 = (uint32_t)rb0 * (uint32_t)p.pitch + (uint32_t)c0;
-                    auto fetch = [&](int base, unit& u) {
+                    auto fetch = [&](int base, unit& u) -> bool {
+                        bool any = false;
 #pragma unroll
                         for (int j = 0; j < DBOT_UNIT_PX; ++j)
                         {
                             const int q = base + 32 * j + lane;
                             u.wb[j] = q < npx ? s_wt[q] : DBOT_W_EMPTY;
-                            const uint32_t rr = ww > 1 ? __umulhi((uint32_t)q, inv_ww) : (uint32_t)q;
-                            u.g[j] = g0 + rr * (uint32_t)p.pitch + ((uint32_t)q - rr * (uint32_t)ww);
+                            any |= u.wb[j] != DBOT_W_EMPTY;
                         }
+                        /* nothing covered in these 32 x DBOT_UNIT_PX entries (window corners, the gap between two
+                         * objects): next */
+                        if (!__any_sync(DBOT_FULL, any)) return false;
 #pragma unroll
                         for (int j = 0; j < DBOT_UNIT_PX; ++j)
                         {
+                            const int q = base + 32 * j + lane;
+                            const uint32_t rr = ww > 1 ? __umulhi((uint32_t)q, inv_ww) : (uint32_t)q;
+                            u.g[j] = g0 + rr * (uint32_t)p.pitch + ((uint32_t)q - rr * (uint32_t)ww);
                             u.tab[j] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
                             u.o_in[j] = 0.f;
                             if (u.wb[j] != DBOT_W_EMPTY)
                             {
-                                s_wt[base + 32 * j + lane] = DBOT_W_EMPTY; /* hand the tile back empty */
+                                s_wt[q] = DBOT_W_EMPTY; /* hand the tile back empty */
                                 u.tab[j] = __ldg(p.tab + u.g[j]);
                                 /* update launches may read a slot whose covered pixels were written
                                  * in an earlier launch phase by its adopter-to-be: L2-coherent, not .nc */
                                 u.o_in[j] = (MODE == DBOT_MODE_UPDATE) ? __ldcg(occ_in + u.g[j]) : __ldg(occ_in + u.g[j]);
                             }
                         }
+                        return true;
                     };
                     auto evaluate = [&](const unit& u) {
                         /* straight-line code for all DBOT_UNIT_PX pixels of the unit: a lane without a covered,
@@ -741,8 +746,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                     for (int base = warp * (32 * DBOT_UNIT_PX); base < npx; base += DBOT_CW * 32 * DBOT_UNIT_PX)
                     {
                         unit ua;
-                        fetch(base, ua);
-                        evaluate(ua);
+                        if (fetch(base, ua)) evaluate(ua);
                     }
                 }
             }

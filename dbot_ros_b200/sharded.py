@@ -137,12 +137,14 @@ class ShardedRbSensor(RbSensor):
         if self.n_slots == 1:
             return sched
         # fast path (the common case): every parent lives on its child's rank
-        idx = np.asarray(indices, dtype=np.int64)
-        c_hi = np.array([shard_bounds(n, self.world, r)[1] for r in range(self.world)])
-        p_hi = np.array([shard_bounds(self.n_slots, self.world, r)[1] for r in range(self.world)])
-        child_rank = np.searchsorted(c_hi, np.arange(n), side="right")
-        parent_rank = np.searchsorted(p_hi, idx, side="right")
-        if np.array_equal(child_rank, parent_rank):
+        key = (n, self.n_slots)
+        if getattr(self, "_sched_key", None) != key:      # the partition tables only change with n / n_slots
+            c_hi = np.array([shard_bounds(n, self.world, r)[1] for r in range(self.world)])
+            self._p_hi = np.array([shard_bounds(self.n_slots, self.world, r)[1] for r in range(self.world)])
+            self._child_rank = np.searchsorted(c_hi, np.arange(n), side="right")
+            self._sched_key = key
+        parent_rank = np.searchsorted(self._p_hi, indices, side="right")
+        if np.array_equal(self._child_rank, parent_rank):
             return sched
         for r in range(self.world):
             lo, hi = shard_bounds(n, self.world, r)

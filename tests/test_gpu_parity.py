@@ -443,3 +443,67 @@ def test_updates_copy_only_touched_rows_and_images_stay_exact():
     assert max(b - a + 1 for a, b in spans) < rows
     sensor.reset()
     assert sensor.slot_rows(0) == (rows, -1)
+
+
+def test_tall_and_wide_triangles_close_to_the_camera():
+    """an 80-triangle icosphere 20-30 cm from a VGA camera: its triangles span 40-300 pixels, i.e. more rows than
+    a span batch lane may own (walked by a warp alone) or more than the int32 edge functions allow (int64 block
+    walk); depth images bit-exact, log-weights within tolerance, with and without culling"""
+    for cull in (True, False):
+        sensor, orc, rows, cols, _ = make_pair("ico80", 1, 8, cull=cull)
+        rng = np.random.default_rng(17)
+        gt = [(synth.rodrigues([0.2, 0.4, -0.1]), np.array([0.01, -0.02, 0.25]))]
+        poses = synth.particle_poses(gt, 8, rng, sigma_t=0.02, sigma_r=0.3)
+        poses[1, 0, 11] = 0.18
+        poses[2, 0, 11] = 0.45
+        for p in poses[:4]:
+            assert np.array_equal(sensor.render(p).view(np.uint32), orc.render(p).view(np.uint32))
+        frame = synth.make_frame(orc.render, gt, rows, cols, rng)
+        for s in (sensor, orc):
+            s.set_observation(frame)
+        ia, ib = np.zeros(8, np.int32), np.zeros(8, np.int32)
+        assert rel_err(sensor.loglikes_poses(poses, ia, True), orc.loglikes_poses(poses, ib, True)) < REL_TOL
+        assert np.max(np.abs(sensor.occlusion(3) - orc.occlusion(3))) < OCC_TOL
+
+
+def test_failed_update_on_the_device_needs_reset():
+    """a parent index that only the device can see to be wrong (device-pointer entry point) fails the update
+    after the slot tables were touched: the error is reported, the handle refuses further work until reset()"""
+    import torch
+
+    n = 12
+    sensor, orc, rows, cols, _ = make_pair("ico80", 8, n)
+    rng = np.random.default_rng(2)
+    gt = [(np.eye(3), np.array([0.0, 0.0, 0.8]))]
+    frame = synth.make_frame(orc.render, gt, rows, cols, rng)
+    poses = synth.particle_poses(gt, n, rng)
+    sensor.set_observation(frame)
+    sensor.loglikes_poses(poses, np.zeros(n, np.int32), True)
+    d_poses = torch.from_numpy(poses).cuda()
+    d_idx = torch.arange(n, dtype=torch.int32, device="cuda")
+    d_idx[5] = 4000                                           # not a slot
+    d_out = torch.zeros(n, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    sensor.loglikes_device(d_poses.data_ptr(), d_idx.data_ptr(), n, True, d_out.data_ptr())
+    with pytest.raises(DbotB200Error) as e:
+        sensor.synchronize()
+    assert e.value.code == -7
+    with pytest.raises(DbotB200Error) as e:
+        sensor.loglikes_poses(poses, np.zeros(n, np.int32), False)
+    assert e.value.code == -13
+    with pytest.raises(DbotB200Error) as e:
+        sensor.set_observation(frame)
+    assert e.value.code == -13
+    sensor.reset()
+    orc.reset()
+    for s in (sensor, orc):
+        s.set_observation(frame)
+    ia, ib = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    assert rel_err(sensor.loglikes_poses(poses, ia, True), orc.loglikes_poses(poses, ib, True)) < REL_TOL
+    # a wrong parent in a call that does not update leaves the handle usable
+    d_idx[:] = torch.arange(n, dtype=torch.int32, device="cuda")
+    d_idx[2] = -1
+    sensor.loglikes_device(d_poses.data_ptr(), d_idx.data_ptr(), n, False, d_out.data_ptr())
+    with pytest.raises(DbotB200Error):
+        sensor.synchronize()
+    assert sensor.loglikes_poses(poses, np.arange(n, dtype=np.int32), False).shape == (n,)
