@@ -312,12 +312,24 @@ def main():
     d_out = torch.zeros(n, dtype=torch.float64, device=dev)
     d_all = torch.zeros(n * world, dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
+    sharded = None
+    if world > 1:
+        # the public multi-GPU API under torchrun: particle-sharded sensor, gather of log-weights inside the
+        # call -- fused into the particle kernel over NVLink peer memory when the ranks can map each other's
+        # memory (csrc/peer_gather.cuh), else one NCCL all-gather
+        from dbot_ros_b200.sharded import ShardedRbSensor, shard_bounds
+
+        sharded = ShardedRbSensor(sensor)
+    fused = sharded is not None and sharded.gather == "fused"
 
     def device_step(k):
         f = k % N_FRAMES
         with torch.cuda.stream(ext):
             d_idx.copy_(d_parents[f], non_blocking=True)   # resampled parents of this frame
             sensor.set_observation_device(d_frames[f].data_ptr())
+            if fused:      # the kernel's epilogue stores the log-weights into every rank's gathered vector
+                sensor.loglikes_gather_device(d_poses[f].data_ptr(), d_idx.data_ptr(), n, True, d_out.data_ptr(), n)
+                return
             sensor.loglikes_device(d_poses[f].data_ptr(), d_idx.data_ptr(), n, True, d_out.data_ptr())
             if world > 1:  # the one exchange of the sharded evaluator: all ranks see all weights
                 dist.all_gather_into_tensor(d_all, d_out)
@@ -366,11 +378,7 @@ def main():
                    "pinned": ([pin(f) for f in frames], [pin(q) for q in poses])}
     idx_host = [p.copy() for p in parents]
     if world > 1:
-        # the public multi-GPU API under torchrun: particle-sharded sensor, all-gather of log-weights inside
-        # the call.  Every rank passes the global arrays; it reads only its own contiguous shard of them.
-        from dbot_ros_b200.sharded import ShardedRbSensor, shard_bounds
-
-        sharded = ShardedRbSensor(sensor)
+        # Every rank passes the global arrays; it reads only its own contiguous shard of them.
         sharded.n_slots = n * world                   # the warm-up above left n slots on every rank
         lo, hi = shard_bounds(n * world, world, rank)
         g_poses, g_parents = [], []
@@ -491,6 +499,12 @@ def main():
                     "value_min": n * world * args.steps / max(e2e_all), "value_max": n * world * args.steps / min(e2e_all)},
             "e2e_pinned": {"value": n * world * args.steps / e2e_pin_s, "unit": UNIT, "host_buffers": "page-locked"},
             "gpu_launches": gpu_launches, "clocks": clocks.summary(), "roofline": roofline}
+    if world > 1:
+        line["gather"] = {"mode": sharded.gather,
+                          "what": "log-weights stored by the particle kernel's epilogue into every rank's gathered "
+                                  "vector (CUDA IPC peer memory over NVLink) + one warp exchanging arrival counters"
+                          if fused else "ncclAllGather through torch.distributed",
+                          "fallback_reason": sharded.gather_reason}
 
     if rank == 0 and world == 1:
         # the same frames through the device-resident filter step (dbot_b200_filter_*): frame in, pose out
@@ -525,7 +539,7 @@ def main():
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "%d of the %d particles per step, %d steps (%.1f s of CPU work), same "
                                           "frames, OpenMP over particles" % (sample, n, reps, sec * reps)}
-    if world > 1:
+    if world > 1 and os.environ.get("DBOT_BENCH_SKIP_SINGLE") != "1":
         # multi-GPU behind the C-ABI (one process, one handle): measured by rank 0 alone while the other ranks
         # wait with idle GPUs.  Weak-scaled config 2 (comparable with this line's value) and, on 8 GPUs or with
         # DBOT_BENCH_CONFIG4=1, BASELINE config 4 at its stated size (8 x 10 000 = 80 000 particles).

@@ -65,6 +65,8 @@ class FilterConfig(C.Structure):
     ]
 
 
+IPC_HANDLE_BYTES = 64   # DBOT_B200_IPC_HANDLE_BYTES
+
 # name -> (restype, argtypes); every symbol include/dbot_b200.h declares
 _P = C.c_void_p
 SIGNATURES = {
@@ -86,6 +88,12 @@ SIGNATURES = {
     "dbot_b200_filter_initialize": (C.c_int, [_P, _P]),
     "dbot_b200_filter_track": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int32)]),
     "dbot_b200_update_empty": (C.c_int, [_P]),
+    "dbot_b200_peer_gather_export": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "dbot_b200_peer_gather_connect": (C.c_int, [_P, _P]),
+    "dbot_b200_loglikes_gather": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "dbot_b200_loglikes_gather_device": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32]),
+    "dbot_b200_peer_gather_result": (_P, [_P]),
+    "dbot_b200_shard_scan": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "dbot_b200_device_count": (C.c_int, [_P]),
     "dbot_b200_migrated_slots": (C.c_int64, [_P]),
     "dbot_b200_n_slots": (C.c_int, [_P]),

@@ -199,6 +199,7 @@ struct dbot_b200_sensor
     int update_since_sync;   /* an update was enqueued through the device-pointer entry points */
     int poisoned;            /* an update failed on the device: the slot tables are half-built, reset() required */
     struct dbot_multi* multi; /* != nullptr: this handle shards its particles over several GPUs (multi_device.cuh) */
+    struct dbot_peer_gather* peer; /* != nullptr: one rank of a process-per-GPU group (peer_gather.cuh) */
 };
 #define DBOT_CHECK_USABLE(s, what)                                                                          \
     do                                                                                                      \
@@ -220,6 +221,8 @@ static int multi_timer_end(dbot_b200_sensor* s, float* out_ms);
 static int multi_n_slots(dbot_b200_sensor* s);
 static dbot_b200_sensor* multi_child(dbot_b200_sensor* s, int g);
 static int multi_count(dbot_b200_sensor* s);
+/* peer_gather.cuh */
+static void peer_gather_close(dbot_b200_sensor* s);
 #define DBOT_SINGLE_ONLY(s, what)                                                                      \
     do                                                                                                 \
     {                                                                                                  \
@@ -402,6 +405,7 @@ extern "C" int dbot_b200_destroy(dbot_b200_sensor* s)
     }
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    peer_gather_close(s);
     cudaFree(s->d_mesh); cudaFree(s->d_chunks); cudaFree(s->d_obs); cudaFree(s->d_tab);
     cudaFree(s->d_pool); cudaFree(s->d_loc[0]); cudaFree(s->d_loc[1]); cudaFree(s->d_free);
     cudaFree(s->d_free_count); cudaFree(s->d_cnt); cudaFree(s->d_last); cudaFree(s->d_pending);
@@ -495,22 +499,28 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     kp.off_XY = off;  off += round_up((uint32_t)max_nv * 8u, 128);
     kp.off_list = off; off += round_up((uint32_t)max_nt * 2u, 128);
     kp.off_wt = off;
-    /* static __shared__ (first-row masks, counters, hand-off) + slack */
-    const int smem_max = (int)prop.sharedMemPerBlockOptin - 1024 - DBOT_CW * 128 - DBOT_CW * 8 - 256;
+    const void* kernels[] = {(const void*)dbot_particle_kernel<DBOT_MODE_EVAL, false>,
+                             (const void*)dbot_particle_kernel<DBOT_MODE_EVAL, true>,
+                             (const void*)dbot_particle_kernel<DBOT_MODE_UPDATE, false>,
+                             (const void*)dbot_particle_kernel<DBOT_MODE_UPDATE, true>,
+                             (const void*)dbot_particle_kernel<DBOT_MODE_RENDER, false>,
+                             (const void*)dbot_particle_kernel<DBOT_MODE_RENDER, true>};
+    /* what the kernels declare as static __shared__ (first-row masks, counters, staged poses, hand-off) comes
+     * off the per-block limit; the rest is the dynamic carve-up */
+    size_t static_max = 0;
+    for (const void* k : kernels)
+    {
+        cudaFuncAttributes fa;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, k));
+        static_max = std::max(static_max, fa.sharedSizeBytes);
+    }
+    const int smem_max = ((int)prop.sharedMemPerBlockOptin - (int)static_max - 64) / 128 * 128;
     if ((int)off + 4 * (int)round_up((uint32_t)kp.cols, 4) > smem_max)
         return fail(-9, "image too wide for the shared-memory depth tile (cols=%d)", kp.cols);
     s->smem_bytes = smem_max;
     kp.wcap = ((uint32_t)(smem_max - (int)off) / 16u) * 4u; /* pixels, multiple of 4 */
-    {
-        const void* kernels[] = {(const void*)dbot_particle_kernel<DBOT_MODE_EVAL, false>,
-                                 (const void*)dbot_particle_kernel<DBOT_MODE_EVAL, true>,
-                                 (const void*)dbot_particle_kernel<DBOT_MODE_UPDATE, false>,
-                                 (const void*)dbot_particle_kernel<DBOT_MODE_UPDATE, true>,
-                                 (const void*)dbot_particle_kernel<DBOT_MODE_RENDER, false>,
-                                 (const void*)dbot_particle_kernel<DBOT_MODE_RENDER, true>};
-        for (const void* k : kernels)
-            CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
-    }
+    for (const void* k : kernels)
+        CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
     s->grid_max = s->num_sms; /* one persistent CTA per SM (launch bounds: 1 CTA/SM) */
 
     /* buffers */
@@ -827,6 +837,9 @@ static int device_error(dbot_b200_sensor* s, const char* what, int was_update)
     if (!code) return 0;
     cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream);
     if (was_update) s->poisoned = 1;
+    if (code == 4)
+        return fail(-16, "%s: a peer rank did not deliver its log-weights within the time limit (did every rank make "
+                         "the same gathering call?)", what);
     if (code == 3) return fail(-11, "%s: an adopting particle timed out waiting for its siblings' copies", what);
     if (code == 2) return fail(-10, "%s: the occlusion-slot pool is exhausted (too many imported slots)", what);
     return fail(-7, "%s: a parent index was not a valid occlusion slot", what);
@@ -1206,6 +1219,7 @@ extern "C" int64_t dbot_b200_device_bytes(dbot_b200_sensor* s)
 
 #include "dbot_filter.cuh"
 #include "multi_device.cuh"
+#include "peer_gather.cuh"
 static int multi_n_slots(dbot_b200_sensor* s) { return s->multi->n_slots; }
 static dbot_b200_sensor* multi_child(dbot_b200_sensor* s, int g) { return s->multi->child[g]; }
 static int multi_count(dbot_b200_sensor* s) { return s->multi->G; }

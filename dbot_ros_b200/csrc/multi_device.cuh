@@ -27,6 +27,10 @@
 #pragma once
 #include <dlfcn.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 /* the handful of NCCL declarations this file needs (bound with dlsym; nccl.h is not required to build) */
@@ -45,6 +49,65 @@ struct dbot_mig_desc
     const int32_t* src_loc; /* the owner's logical -> physical table */
     int32_t src_slot;       /* logical slot on the owner */
     int32_t pad;
+};
+
+/* One host thread per shard beyond the first, alive as long as the handle: it keeps its GPU current and
+ * enqueues that shard's copies and kernels while the caller's thread does shard 0's.  Done from a single
+ * thread, the last GPU of eight would start half a millisecond late; started per call, seven thread creations
+ * cost a quarter of a millisecond.  A worker spins for the next job for a short while after finishing one (the
+ * calls of a frame come back to back), then sleeps on a condition variable. */
+struct dbot_shard_worker
+{
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<void()> job;
+    std::atomic<int> posted{0}, finished{0};
+    bool quit = false;
+
+    void loop(int device)
+    {
+        cudaSetDevice(device);
+        int seen = 0;
+        for (;;)
+        {
+            for (int spin = 0; spin < 40000 && posted.load(std::memory_order_acquire) == seen; ++spin)
+                __builtin_ia32_pause();
+            if (posted.load(std::memory_order_acquire) == seen)
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return quit || posted.load(std::memory_order_acquire) != seen; });
+                if (quit) return;
+            }
+            seen = posted.load(std::memory_order_acquire);
+            job();
+            finished.store(seen, std::memory_order_release);
+        }
+    }
+    void post(std::function<void()> j)
+    {
+        job = std::move(j);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            posted.fetch_add(1, std::memory_order_release);
+        }
+        cv.notify_one();
+    }
+    void wait()
+    {
+        const int want = posted.load(std::memory_order_acquire);
+        while (finished.load(std::memory_order_acquire) != want) __builtin_ia32_pause();
+    }
+    void stop()
+    {
+        if (!th.joinable()) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+        }
+        cv.notify_one();
+        th.join();
+    }
 };
 
 struct dbot_multi
@@ -79,7 +142,17 @@ struct dbot_multi
     dbot_mig_desc* h_mig[DBOT_B200_MAX_DEVICES];
     int64_t migrated;
     std::vector<int32_t>* local_idx;
+    dbot_shard_worker* worker[DBOT_B200_MAX_DEVICES]; /* [0] unused: shard 0 runs on the caller's thread */
 };
+
+/* run fn(g) for every shard: shard 0 on this thread, the others on their workers; returns when all are done */
+template <class F>
+static void multi_for_each_shard(dbot_multi* m, F fn)
+{
+    for (int g = 1; g < m->G; ++g) m->worker[g]->post([fn, g] { fn(g); });
+    fn(0);
+    for (int g = 1; g < m->G; ++g) m->worker[g]->wait();
+}
 
 /* pop n_mig free physical slots for the logical slots first .. first + n_mig - 1 */
 __global__ void dbot_import_pop_many_kernel(int32_t* loc, const int32_t* free_stack, int32_t* free_count, int first,
@@ -134,6 +207,12 @@ static int multi_destroy(dbot_b200_sensor* s)
 {
     dbot_multi* m = s->multi;
     if (!m) return 0;
+    for (int g = 1; g < m->G; ++g)
+        if (m->worker[g])
+        {
+            m->worker[g]->stop();
+            delete m->worker[g];
+        }
     for (int g = 0; g < m->G; ++g)
     {
         if (!m->child[g]) continue;
@@ -253,6 +332,13 @@ static int multi_create(const dbot_b200_config* cfg, dbot_b200_sensor* s)
         if (nrc != 0) return fail(-14, "ncclCommInitAll failed: %s", m->GetErrorString(nrc));
         m->have_comms = 1;
     }
+    for (int g = 1; g < G; ++g)
+    {
+        m->worker[g] = new dbot_shard_worker();
+        dbot_shard_worker* w = m->worker[g];
+        const int device = m->dev[g];
+        w->th = std::thread([w, device] { w->loop(device); });
+    }
     m->n_slots = 1;
     m->prev_cnt = 1;
     m->fresh = 1;
@@ -287,15 +373,25 @@ static int multi_set_observation(dbot_b200_sensor* s, const float* depth_m)
         if (rc) return rc;
     }
     memcpy(m->h_obs, depth_m, bytes);
-    for (int g = 0; g < m->G; ++g)
-    {
+    int shard_rc[DBOT_B200_MAX_DEVICES] = {0};
+    std::string shard_err[DBOT_B200_MAX_DEVICES];
+    multi_for_each_shard(m, [&](int g) {
         dbot_b200_sensor* c = m->child[g];
-        CUDA_TRY(cudaSetDevice(m->dev[g]));
-        CUDA_TRY(cudaMemcpyAsync(c->d_obs, m->h_obs, bytes, cudaMemcpyHostToDevice, c->stream));
-        int rc = launch_observation(c, c->d_obs);
-        if (rc) return rc;
-    }
+        auto body = [&]() -> int {
+            CUDA_TRY(cudaSetDevice(m->dev[g]));
+            CUDA_TRY(cudaMemcpyAsync(c->d_obs, m->h_obs, bytes, cudaMemcpyHostToDevice, c->stream));
+            return launch_observation(c, c->d_obs);
+        };
+        shard_rc[g] = body();
+        if (shard_rc[g]) shard_err[g] = g_last_error; /* thread-local: carried back to the caller's thread */
+    });
     m->obs_in_flight = 1;
+    for (int g = 0; g < m->G; ++g)
+        if (shard_rc[g])
+        {
+            g_last_error = shard_err[g];
+            return shard_rc[g];
+        }
     return 0;
 }
 
@@ -381,8 +477,7 @@ static int multi_loglikes(dbot_b200_sensor* s, const float* poses, int32_t* indi
     const int32_t* local = m->local_idx->data();
     const size_t pose_stride = (size_t)12 * s->kp.n_obj;
     int cnt = (n + G - 1) / G;
-    /* one host thread per shard stages that shard's slice and enqueues its copies and kernels: done one
-     * after the other from a single thread, the last GPU of eight would start half a millisecond late */
+    /* every shard's thread stages that shard's slice and enqueues its copies and kernels */
     int shard_rc[DBOT_B200_MAX_DEVICES] = {0};
     std::string shard_err[DBOT_B200_MAX_DEVICES];
     auto enqueue_shard = [&](int g) {
@@ -406,12 +501,7 @@ static int multi_loglikes(dbot_b200_sensor* s, const float* poses, int32_t* indi
         shard_rc[g] = body();
         if (shard_rc[g]) shard_err[g] = g_last_error; /* thread-local: carried back to the caller's thread */
     };
-    {
-        std::thread workers[DBOT_B200_MAX_DEVICES];
-        for (int g = 1; g < G; ++g) workers[g] = std::thread(enqueue_shard, g);
-        enqueue_shard(0);
-        for (int g = 1; g < G; ++g) workers[g].join();
-    }
+    multi_for_each_shard(m, enqueue_shard);
     for (int g = 0; g < G; ++g)
         if (shard_rc[g])
         {
@@ -445,15 +535,16 @@ static int multi_loglikes(dbot_b200_sensor* s, const float* poses, int32_t* indi
                              m->child[0]->stream));
     int first_error = 0;
     std::string first_text;
+    multi_for_each_shard(m, [&](int g) { /* error flags back, wait: every shard on its own thread */
+        shard_rc[g] = loglikes_finish(m->child[g], 0, update, nullptr);
+        if (shard_rc[g]) shard_err[g] = g_last_error;
+    });
     for (int g = 0; g < G; ++g)
-    {
-        rc = loglikes_finish(m->child[g], 0, update, nullptr);
-        if (rc && !first_error)
+        if (shard_rc[g] && !first_error)
         {
-            first_error = rc;
-            first_text = g_last_error;
+            first_error = shard_rc[g];
+            first_text = shard_err[g];
         }
-    }
     m->obs_in_flight = 0;
     if (first_error)
     {

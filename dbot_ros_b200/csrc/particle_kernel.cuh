@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
         mbar_init(&s_bar, 1);
         mbar_fence_init();
         s_copied = 0;
+        s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0;
     }
     __syncthreads();
 
@@ -460,16 +461,31 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
 #pragma unroll
         for (int e = 0; e < 12; ++e) pose[e] = __ldg(pose_g + e);
         const float4* vg = reinterpret_cast<const float4*>(p.mesh + ch.vert_off);
-        for (int v = tid; v < ch.n_verts; v += DBOT_CT)
+        /* four vertices per thread and step, all four loads in flight before the first is used */
+        for (int v0 = tid; v0 < ch.n_verts; v0 += 4 * DBOT_CT)
         {
-            const float4 o = __ldg(vg + v);
-            const dbot_vertex t = dbot_transform_vertex(o.x, o.y, o.z, pose, p.K);
-            s_v4[v] = make_float4(t.x, t.y, t.z, t.iz);
-            s_XY[v] = make_int2(t.X, t.Y);
-            if (t.X != DBOT_VERT_INVALID)
+            float4 o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
             {
-                mnx = min(mnx, t.X); mxx = max(mxx, t.X);
-                mny = min(mny, t.Y); mxy = max(mxy, t.Y);
+                const int v = v0 + u * DBOT_CT;
+                o[u] = __ldg(vg + (v < ch.n_verts ? v : v0));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+                const int v = v0 + u * DBOT_CT;
+                if (v < ch.n_verts)
+                {
+                    const dbot_vertex t = dbot_transform_vertex(o[u].x, o[u].y, o[u].z, pose, p.K);
+                    s_v4[v] = make_float4(t.x, t.y, t.z, t.iz);
+                    s_XY[v] = make_int2(t.X, t.Y);
+                    if (t.X != DBOT_VERT_INVALID)
+                    {
+                        mnx = min(mnx, t.X); mxx = max(mxx, t.X);
+                        mny = min(mny, t.Y); mxy = max(mxy, t.Y);
+                    }
+                }
             }
         }
     };
@@ -613,15 +629,19 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
              * width, or -- when the window is wider than tall, e.g. several objects side by side --
              * column bands of the full height, so that a tile meets as few mesh chunks as possible. */
             const int wc0 = c0, wc1 = c1, wh = r1 - r0 + 1;
-            int tile_rows = max(1, (int)(p.wcap / (uint32_t)ww)), tile_cols = ww;
-            if (MULTI && tile_rows < wh && ww > wh && (uint32_t)wh * 32u <= p.wcap)
+            int tile_rows = wh, tile_cols = ww; /* the usual case: the whole window is one tile */
+            if ((uint32_t)ww * (uint32_t)wh > p.wcap)
             {
-                tile_rows = wh;
-                tile_cols = (int)(p.wcap / (uint32_t)wh);
+                tile_rows = max(1, (int)(p.wcap / (uint32_t)ww));
+                if (MULTI && tile_rows < wh && ww > wh && (uint32_t)wh * 32u <= p.wcap)
+                {
+                    tile_rows = wh;
+                    tile_cols = (int)(p.wcap / (uint32_t)wh);
+                }
+                /* as few tiles as the capacity allows, of equal size: every tile costs a prepass over the mesh */
+                tile_rows = (wh + (wh + tile_rows - 1) / tile_rows - 1) / ((wh + tile_rows - 1) / tile_rows);
+                tile_cols = (ww + (ww + tile_cols - 1) / tile_cols - 1) / ((ww + tile_cols - 1) / tile_cols);
             }
-            /* as few tiles as the capacity allows, of equal size: every tile costs a prepass over the mesh */
-            tile_rows = (wh + (wh + tile_rows - 1) / tile_rows - 1) / ((wh + tile_rows - 1) / tile_rows);
-            tile_cols = (ww + (ww + tile_cols - 1) / tile_cols - 1) / ((ww + tile_cols - 1) / tile_cols);
             for (int rb0 = r0; rb0 <= r1; rb0 += tile_rows)
             for (int cb0 = wc0; cb0 <= wc1; cb0 += tile_cols)
             {
@@ -630,8 +650,9 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                 if (!MULTI)
                 {
                     stage_chunk(0); /* resident after the first particle */
-                    if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; }
-                    compute_sync(); /* counters published; every warp is done with the previous tile */
+                    /* the raster counters were put back to zero when the previous sweep ended (below); a
+                     * particle's first tile comes after the window barrier, later ones need their own */
+                    if (rb0 != r0 || cb0 != wc0) compute_sync();
                     DBOT_TL();
                     dbot_raster_prepass(S, p.chunks[0].n_tris, p.chunks[0].cull_sign, rb0, rb1, c0, c1, tid);
                     compute_sync();
@@ -662,6 +683,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                     }
                 }
                 compute_sync();
+                if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; } /* every warp has left the sweep */
                 if (MODE == DBOT_MODE_UPDATE && !copied) await_slot();
                 /* ---- per-pixel mixture over the band: a warp per row, DBOT_UNIT_PX x 32 columns
                  * (and their loads) in flight per step ---- */

@@ -331,6 +331,37 @@ class B200KinectImageModel(RbSensor):
         abi.check(self._lib, self._lib.dbot_b200_import_slot_device(self._h, C.c_void_p(d_src_ptr), C.byref(out)))
         return out.value
 
+    # -- gather of log-weights over NVLink peer memory, one process per GPU (csrc/peer_gather.cuh) ---
+    def peer_gather_export(self, world, rank, width_max):
+        """allocate this rank's gathered vectors; returns the 64-byte CUDA IPC handle the other ranks need"""
+        handle = C.create_string_buffer(abi.IPC_HANDLE_BYTES)
+        abi.check(self._lib, self._lib.dbot_b200_peer_gather_export(
+            self._h, int(world), int(rank), int(width_max), C.cast(handle, C.c_void_p)))
+        return handle.raw
+
+    def peer_gather_connect(self, handles):
+        """handles: the world exported handles in rank order"""
+        blob = b"".join(handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        abi.check(self._lib, self._lib.dbot_b200_peer_gather_connect(self._h, C.cast(buf, C.c_void_p)))
+
+    def loglikes_gather(self, poses_local, indices_local, update, width, out_all):
+        """this rank's slice in, every rank's log-weights out (out_all: float64[world * width], written)"""
+        n = int(indices_local.shape[0])
+        abi.check(self._lib, self._lib.dbot_b200_loglikes_gather(
+            self._h, abi.ptr(poses_local) if n else None, abi.ptr(indices_local) if n else None, n,
+            1 if update else 0, int(width), abi.ptr(out_all)))
+
+    def loglikes_gather_device(self, d_poses_ptr, d_indices_ptr, n_local, update, d_out_ptr, width):
+        abi.check(self._lib, self._lib.dbot_b200_loglikes_gather_device(
+            self._h, C.c_void_p(d_poses_ptr), C.c_void_p(d_indices_ptr), int(n_local), 1 if update else 0,
+            C.c_void_p(d_out_ptr), int(width)))
+
+    @property
+    def peer_gather_result(self):
+        """device pointer of the gathered vector the last gathering call filled"""
+        return self._lib.dbot_b200_peer_gather_result(self._h)
+
     @property
     def stream(self):
         return self._lib.dbot_b200_stream(self._h)

@@ -22,6 +22,9 @@ test-suite injects the oracle to check the host logic under gloo.
 """
 from __future__ import annotations
 
+import ctypes
+import os
+
 import numpy as np
 
 from .rb_sensor import RbSensor
@@ -69,6 +72,9 @@ class ShardedRbSensor(RbSensor):
         self.allow_migration = allow_migration
         self.n_slots = 1          # global slot count; after reset every rank holds slot 0
         self._buf = None
+        self._out_all = None
+        lib = getattr(local_sensor, "_lib", None)
+        self._scan = getattr(lib, "dbot_b200_shard_scan", None)
         # parents imported since the last update: for EVERY rank the set of global slots it holds a
         # copy of (all ranks track all sets: the schedule must come out the same everywhere), and for
         # this rank the local slot index of each
@@ -78,6 +84,43 @@ class ShardedRbSensor(RbSensor):
         from .rb_sensor import _LIVE_WRAPPERS
 
         _LIVE_WRAPPERS.add(self)
+        self.gather = "collective"   # or "fused": peer stores from the particle kernel (csrc/peer_gather.cuh)
+        self.gather_reason = None
+        self._connect_peers()
+
+    def _connect_peers(self):
+        """GPUs: share every rank's gathered vector with every other rank as CUDA IPC memory, so that the particle
+        kernel's epilogue stores the log-weights straight into all of them over NVLink and no collective is
+        launched per call.  Collective itself (every rank constructs its ShardedRbSensor); all ranks end up in the
+        same mode: if one of them cannot map a peer, all use the NCCL all-gather."""
+        import torch.distributed as dist
+
+        if self.device.type != "cuda" or not hasattr(self.local, "peer_gather_export") or self.world < 2:
+            return
+        if os.environ.get("DBOT_B200_SHARDED_GATHER", "fused") != "fused":
+            self.gather_reason = "DBOT_B200_SHARDED_GATHER asks for the collective"
+            return
+        width_max = int(getattr(self.local, "max_sample_count"))
+        handle, why = b"", None
+        try:
+            handle = self.local.peer_gather_export(self.world, self.rank, width_max)
+        except Exception as e:  # noqa: BLE001 -- any failure means "use the collective", on every rank
+            why = str(e)
+        got = [None] * self.world
+        dist.all_gather_object(got, (handle, why), group=self.group)
+        if all(h for h, _ in got):
+            try:
+                self.local.peer_gather_connect([h for h, _ in got])
+            except Exception as e:  # noqa: BLE001
+                why = str(e)
+        else:
+            why = why or next(w for h, w in got if not h)
+        agreed = [None] * self.world
+        dist.all_gather_object(agreed, why, group=self.group)
+        if all(w is None for w in agreed):
+            self.gather = "fused"
+        else:
+            self.gather_reason = next(w for w in agreed if w is not None)
 
     def close(self):
         """Release the torch buffers that were used on the local sensor's stream while that stream still exists:
@@ -302,17 +345,42 @@ class ShardedRbSensor(RbSensor):
         got = self._h_all[: width * self.world].numpy().reshape(self.world, width)
         return np.concatenate([got[r, : counts[r]] for r in range(self.world)])
 
+    def _evaluate_and_gather_fused(self, poses, lo, hi, local_idx, n, update):
+        """CUDA path with mapped peers: one library call stages this rank's slice, runs the particle kernel --
+        whose epilogue stores every log-weight into every rank's gathered vector over NVLink --, exchanges the
+        arrival counters and copies the gathered vector back.  No torch op, no collective launch."""
+        width = -(-n // self.world)
+        if self._out_all is None or self._out_all.size != width * self.world:
+            self._out_all = np.empty(width * self.world, dtype=np.float64)
+        self.local.loglikes_gather(poses[lo:hi], np.ascontiguousarray(local_idx, dtype=np.int32), update, width,
+                                   self._out_all)
+        if n == width * self.world:
+            return self._out_all.copy()
+        counts = shard_counts(n, self.world)
+        got = self._out_all.reshape(self.world, width)
+        return np.concatenate([got[r, : counts[r]] for r in range(self.world)])
+
     def loglikes_poses(self, poses, indices, update=False):
         n_obj = self.local.n_objects
         poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, n_obj, 12)
         n = poses.shape[0]
         if not (isinstance(indices, np.ndarray) and indices.dtype == np.int32 and indices.size == n):
             raise TypeError("loglikes: indices must be an int32 numpy array with one entry per state")
-        if np.any(indices < 0) or np.any(indices >= self.n_slots):
-            raise IndexError("loglikes: parent slot out of range (have %d)" % self.n_slots)
-        self.migrate(indices, n)
+        if self._scan is not None and indices.flags.c_contiguous:
+            # the library's one pass over the parents: range check + "does any child need a remote parent?"
+            rc = self._scan(indices.ctypes.data_as(ctypes.c_void_p), n, self.n_slots, self.world, None)
+            if rc < 0:
+                raise IndexError("loglikes: parent slot out of range (have %d)" % self.n_slots)
+            if rc == 1:
+                self.migrate(indices, n)
+        else:
+            if np.any(indices < 0) or np.any(indices >= self.n_slots):
+                raise IndexError("loglikes: parent slot out of range (have %d)" % self.n_slots)
+            self.migrate(indices, n)
         lo, hi, local_idx = self.local_parents(indices, n)
-        if self.device.type == "cuda" and hasattr(self.local, "loglikes_device"):
+        if self.gather == "fused":
+            out = self._evaluate_and_gather_fused(poses, lo, hi, local_idx, n, update)
+        elif self.device.type == "cuda" and hasattr(self.local, "loglikes_device"):
             out = self._evaluate_and_gather_on_device(poses, lo, hi, local_idx, n, update)
         else:
             if hi > lo:

@@ -159,6 +159,32 @@ int dbot_b200_filter_track(dbot_b200_filter* f, const float* depth_m, double* ou
  * of a call in which this shard received no particle -- every slot is given back and the handle's update clock
  * advances as on the other shards */
 int dbot_b200_update_empty(dbot_b200_sensor* s);
+/* ---- the gather of log-weights for one process per GPU, fused into the particle kernel over NVLink peer
+ * memory (csrc/peer_gather.cuh; SURVEY.md section 8e asks for ONE all-gather of log-weights per call -- here the
+ * kernel's epilogue stores every log-weight straight into every rank's gathered vector, shared between the
+ * processes as CUDA IPC memory, and one warp exchanges arrival counters; no collective is launched).
+ *   export   allocates this rank's gathered vectors for slices of up to width_max particles and returns the
+ *            DBOT_B200_IPC_HANDLE_BYTES-byte handle the other ranks need;
+ *   connect  takes all world handles (rank order, this rank's own entry is ignored) and maps the peers;
+ *   loglikes_gather         RbSensor::loglikes on this rank's slice (host arrays, parents in this rank's own
+ *            slot numbering); out_all[g * width + i] = log-weight of particle i of rank g's slice, for all
+ *            ranks.  Every rank must make the same sequence of gathering calls (n_local may be 0);
+ *   loglikes_gather_device  the same with device pointers and no wait; the gathered vector is at
+ *            peer_gather_result() once the stream has run (valid until the next gathering call but one).
+ * Errors: -15 a peer's memory cannot be mapped, -16 a peer did not arrive within about 10 s. ---- */
+#define DBOT_B200_IPC_HANDLE_BYTES 64
+int dbot_b200_peer_gather_export(dbot_b200_sensor* s, int32_t world, int32_t rank, int32_t width_max,
+                                 void* out_handle);
+int dbot_b200_peer_gather_connect(dbot_b200_sensor* s, const void* handles);
+int dbot_b200_loglikes_gather(dbot_b200_sensor* s, const float* poses_local, const int32_t* indices_local,
+                              int32_t n_local, int32_t update, int32_t width, double* out_all);
+int dbot_b200_loglikes_gather_device(dbot_b200_sensor* s, const float* d_poses, int32_t* d_indices,
+                                     int32_t n_local, int32_t update, double* d_out, int32_t width);
+void* dbot_b200_peer_gather_result(dbot_b200_sensor* s);
+/* host-side check of a sharded call's global parent vector: 0 = every child's parent lives on the child's own
+ * rank, 1 = not (out_first: the first such child), -7 = a parent is not a slot.  Ranks own contiguous balanced
+ * slices of the n particles and of the n_slots slots (the first n % world ranks hold one more). */
+int dbot_b200_shard_scan(const int32_t* indices, int32_t n, int32_t n_slots, int32_t world, int32_t* out_first);
 /* number of GPUs behind the handle; occlusion slots that have moved between them since create */
 int dbot_b200_device_count(dbot_b200_sensor* s);
 int64_t dbot_b200_migrated_slots(dbot_b200_sensor* s);

@@ -89,3 +89,45 @@ def test_rotation_matrices_and_compose():
     with pytest.raises(ValueError):
         s.compose(np.zeros((3, 14)))
     s._h = None  # nothing to destroy
+
+
+def test_shard_scan_agrees_with_the_python_partition():
+    """dbot_b200_shard_scan (the one pass over a sharded call's parent vector, host code in the library) against
+    shard_bounds / shard_owner: same owners, first remote child, range errors"""
+    import ctypes
+
+    from dbot_ros_b200 import abi
+    from dbot_ros_b200.sharded import shard_bounds, shard_owner
+
+    lib = abi.load_library()
+    rng = np.random.default_rng(3)
+    for n, n_slots, world in [(10, 10, 2), (501, 501, 2), (7, 3, 8), (1000, 997, 8), (5, 1, 4), (8000, 8000, 8)]:
+        child_owner = np.array([shard_owner(i, n, world) for i in range(n)])
+        for r in range(world):
+            lo, hi = shard_bounds(n, world, r)
+            assert np.all(child_owner[lo:hi] == r)
+        # every parent on its child's rank
+        idx = np.empty(n, dtype=np.int32)
+        ok = True
+        for i in range(n):
+            lo, hi = shard_bounds(n_slots, world, child_owner[i])
+            if hi == lo:
+                ok = False
+                idx[i] = 0
+            else:
+                idx[i] = rng.integers(lo, hi)
+        first = ctypes.c_int32(-2)
+        rc = lib.dbot_b200_shard_scan(abi.ptr(idx), n, n_slots, world, ctypes.byref(first))
+        want = [i for i in range(n) if n_slots > 1 and shard_owner(int(idx[i]), n_slots, world) != child_owner[i]]
+        assert rc == (1 if want else 0) and first.value == (want[0] if want else -1)
+        if ok and n_slots > 1:
+            assert rc == 0
+        # one child with a parent somewhere else
+        idx2 = rng.integers(0, n_slots, size=n).astype(np.int32)
+        rc = lib.dbot_b200_shard_scan(abi.ptr(idx2), n, n_slots, world, ctypes.byref(first))
+        want = [i for i in range(n) if n_slots > 1 and shard_owner(int(idx2[i]), n_slots, world) != child_owner[i]]
+        assert rc == (1 if want else 0) and first.value == (want[0] if want else -1)
+        idx2[n // 2] = n_slots
+        assert lib.dbot_b200_shard_scan(abi.ptr(idx2), n, n_slots, world, None) == -7
+        idx2[n // 2] = -1
+        assert lib.dbot_b200_shard_scan(abi.ptr(idx2), n, n_slots, world, None) == -7

@@ -27,6 +27,7 @@ rows, cols = synth.resolution(ds); K = synth.camera_matrix(ds); V, T = synth.mes
 build = lambda cnt, dev: RbSensorBuilder(ObjectModel(V, T), CameraData(K, rows, cols), Parameters(sample_count=cnt), device_id=dev).build()
 local = build(n, lr)
 sharded = ShardedRbSensor(local)
+print("rank %d gather: %s (%s)" % (rank, sharded.gather, sharded.gather_reason), flush=True)
 single = build(n, lr) if rank == 0 else None
 rng = np.random.default_rng(5)
 gt = synth.ground_truth_poses(1, rng)
@@ -62,19 +63,23 @@ sys.exit(0 if int(flag.item()) == 1 else 3)
 '''
 
 
-def test_two_gpu_sharding_is_bit_identical(tmp_path):
+@pytest.mark.parametrize("gather", ["fused", "collective"])
+def test_two_gpu_sharding_is_bit_identical(tmp_path, gather):
+    """gather = fused: the particle kernel stores the log-weights into both ranks' gathered vectors (CUDA IPC
+    memory over NVLink, csrc/peer_gather.cuh); collective: ncclAllGather through torch.distributed"""
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, DBOT_ROOT=os.path.dirname(HERE))
+    env = dict(os.environ, DBOT_ROOT=os.path.dirname(HERE), DBOT_B200_SHARDED_GATHER=gather)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "bit-identical to one GPU: True" in r.stdout, r.stdout[-2000:]
+    assert "rank 0 gather: %s" % gather in r.stdout and "rank 1 gather: %s" % gather in r.stdout, r.stdout[-2000:]
     print(r.stdout[-600:])
 
 
