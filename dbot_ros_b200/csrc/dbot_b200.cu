@@ -59,6 +59,7 @@
 #define DBOT_STREAM_REGS 56
 #define DBOT_COMPUTE_REGS 72
 #endif
+#define DBOT_STAGERS 2             /* host threads beside the caller's that stage a pageable depth frame */
 #define DBOT_CHUNK_MAX_VERTS 3072
 #define DBOT_CHUNK_MAX_TRIS 6144
 #define DBOT_FULL 0xffffffffu
@@ -115,6 +116,7 @@ struct dbot_kparams
     uint32_t wcap;          /* inverse-depth tile capacity in pixels */
 };
 
+#include "host_workers.cuh"
 #include "ptx_wrappers.cuh"
 #include "state_kernels.cuh"
 #include "particle_kernel.cuh"
@@ -200,6 +202,7 @@ struct dbot_b200_sensor
     int poisoned;            /* an update failed on the device: the slot tables are half-built, reset() required */
     struct dbot_multi* multi; /* != nullptr: this handle shards its particles over several GPUs (multi_device.cuh) */
     struct dbot_peer_gather* peer; /* != nullptr: one rank of a process-per-GPU group (peer_gather.cuh) */
+    dbot_shard_worker* stager[DBOT_STAGERS]; /* helpers that copy thirds of a pageable depth frame into h_obs */
 };
 #define DBOT_CHECK_USABLE(s, what)                                                                          \
     do                                                                                                      \
@@ -406,6 +409,12 @@ extern "C" int dbot_b200_destroy(dbot_b200_sensor* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     peer_gather_close(s);
+    for (int k = 0; k < DBOT_STAGERS; ++k)
+        if (s->stager[k])
+        {
+            s->stager[k]->stop();
+            delete s->stager[k];
+        }
     cudaFree(s->d_mesh); cudaFree(s->d_chunks); cudaFree(s->d_obs); cudaFree(s->d_tab);
     cudaFree(s->d_pool); cudaFree(s->d_loc[0]); cudaFree(s->d_loc[1]); cudaFree(s->d_free);
     cudaFree(s->d_free_count); cudaFree(s->d_cnt); cudaFree(s->d_last); cudaFree(s->d_pending);
@@ -680,6 +689,19 @@ static int launch_observation(dbot_b200_sensor* s, const float* d_depth)
 }
 
 /* page-locked host memory can be handed to the copy engine as it is */
+/* the helpers that stage pageable depth frames are started with the first such frame */
+static void ensure_stagers(dbot_b200_sensor* s)
+{
+    if (s->stager[0]) return;
+    for (int k = 0; k < DBOT_STAGERS; ++k)
+    {
+        dbot_shard_worker* w = new dbot_shard_worker();
+        w->spin = 4000; /* frames are a third of a millisecond apart at best: sleep between them */
+        w->th = std::thread([w] { w->loop(-1); });
+        s->stager[k] = w;
+    }
+}
+
 static bool is_pinned_host(const void* p)
 {
     cudaPointerAttributes a;
@@ -712,14 +734,30 @@ extern "C" int dbot_b200_set_observation(dbot_b200_sensor* s, const float* depth
      * running -- every later call on this handle is ordered behind them on the same stream, and the
      * staging buffer is not touched again before they are done */
     if (s->obs_in_flight) CUDA_TRY(cudaEventSynchronize(s->ev_obs));
-    /* in four pieces, so that the copy engine moves one piece while the host stages the next */
+    /* in pieces: the helpers stage theirs while this thread stages the first, and the copy engine moves a piece
+     * while the next one is still being staged */
     const size_t total = (size_t)s->kp.rows * s->kp.cols;
-    for (int piece = 0; piece < 4; ++piece)
+    const int pieces = total >= 65536 ? DBOT_STAGERS + 1 : 1;
+    if (pieces > 1) ensure_stagers(s);
+    for (int piece = 1; piece < pieces; ++piece)
     {
-        const size_t a = total * piece / 4, b = total * (piece + 1) / 4;
-        memcpy(s->h_obs + a, depth_m + a, (b - a) * sizeof(float));
-        CUDA_TRY(cudaMemcpyAsync(s->d_obs + a, s->h_obs + a, (b - a) * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        const size_t a = total * piece / pieces, b = total * (piece + 1) / pieces;
+        float* dst = s->h_obs + a;
+        const float* src = depth_m + a;
+        s->stager[piece - 1]->post([dst, src, a, b] { memcpy(dst, src, (b - a) * sizeof(float)); });
     }
+    cudaError_t copy_err = cudaSuccess;
+    for (int piece = 0; piece < pieces; ++piece)
+    {
+        const size_t a = total * piece / pieces, b = total * (piece + 1) / pieces;
+        if (piece == 0)
+            memcpy(s->h_obs + a, depth_m + a, (b - a) * sizeof(float));
+        else
+            s->stager[piece - 1]->wait(); /* always: no job may outlive this call (it reads the caller's buffer) */
+        if (copy_err == cudaSuccess)
+            copy_err = cudaMemcpyAsync(s->d_obs + a, s->h_obs + a, (b - a) * sizeof(float), cudaMemcpyHostToDevice, s->stream);
+    }
+    CUDA_TRY(copy_err);
     CUDA_TRY(cudaEventRecord(s->ev_obs, s->stream));
     s->obs_in_flight = 1;
     return launch_observation(s, s->d_obs);

@@ -1,0 +1,71 @@
+/*
+ * host_workers.cuh -- a host thread that runs posted jobs (shard enqueues in multi_device.cuh, staging copies of
+ * pageable depth frames in dbot_b200.cu).  Part of libdbot_b200.so; included by dbot_b200.cu.
+ */
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+
+/* Alive as long as the handle that owns it.  multi_device.cuh keeps one per shard beyond the first: it keeps its
+ * GPU current and enqueues that shard's copies and kernels while the caller's thread does shard 0's (done from a
+ * single thread, the last GPU of eight would start half a millisecond late; started per call, seven thread
+ * creations cost a quarter of a millisecond).  A worker spins for the next job for `spin` polls after finishing
+ * one (the calls of a frame come back to back), then sleeps on a condition variable. */
+struct dbot_shard_worker
+{
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<void()> job;
+    std::atomic<int> posted{0}, finished{0};
+    bool quit = false;
+    int spin = 40000;
+
+    void loop(int device) /* device < 0: a plain host worker */
+    {
+        if (device >= 0) cudaSetDevice(device);
+        int seen = 0;
+        for (;;)
+        {
+            for (int k = 0; k < spin && posted.load(std::memory_order_acquire) == seen; ++k)
+                __builtin_ia32_pause();
+            if (posted.load(std::memory_order_acquire) == seen)
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return quit || posted.load(std::memory_order_acquire) != seen; });
+                if (quit) return;
+            }
+            seen = posted.load(std::memory_order_acquire);
+            job();
+            finished.store(seen, std::memory_order_release);
+        }
+    }
+    void post(std::function<void()> j)
+    {
+        job = std::move(j);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            posted.fetch_add(1, std::memory_order_release);
+        }
+        cv.notify_one();
+    }
+    void wait()
+    {
+        const int want = posted.load(std::memory_order_acquire);
+        while (finished.load(std::memory_order_acquire) != want) __builtin_ia32_pause();
+    }
+    void stop()
+    {
+        if (!th.joinable()) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+        }
+        cv.notify_one();
+        th.join();
+    }
+};
+

@@ -27,10 +27,6 @@
 #pragma once
 #include <dlfcn.h>
 
-#include <atomic>
-#include <condition_variable>
-#include <functional>
-#include <mutex>
 #include <thread>
 
 /* the handful of NCCL declarations this file needs (bound with dlsym; nccl.h is not required to build) */
@@ -49,65 +45,6 @@ struct dbot_mig_desc
     const int32_t* src_loc; /* the owner's logical -> physical table */
     int32_t src_slot;       /* logical slot on the owner */
     int32_t pad;
-};
-
-/* One host thread per shard beyond the first, alive as long as the handle: it keeps its GPU current and
- * enqueues that shard's copies and kernels while the caller's thread does shard 0's.  Done from a single
- * thread, the last GPU of eight would start half a millisecond late; started per call, seven thread creations
- * cost a quarter of a millisecond.  A worker spins for the next job for a short while after finishing one (the
- * calls of a frame come back to back), then sleeps on a condition variable. */
-struct dbot_shard_worker
-{
-    std::thread th;
-    std::mutex mu;
-    std::condition_variable cv;
-    std::function<void()> job;
-    std::atomic<int> posted{0}, finished{0};
-    bool quit = false;
-
-    void loop(int device)
-    {
-        cudaSetDevice(device);
-        int seen = 0;
-        for (;;)
-        {
-            for (int spin = 0; spin < 40000 && posted.load(std::memory_order_acquire) == seen; ++spin)
-                __builtin_ia32_pause();
-            if (posted.load(std::memory_order_acquire) == seen)
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return quit || posted.load(std::memory_order_acquire) != seen; });
-                if (quit) return;
-            }
-            seen = posted.load(std::memory_order_acquire);
-            job();
-            finished.store(seen, std::memory_order_release);
-        }
-    }
-    void post(std::function<void()> j)
-    {
-        job = std::move(j);
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            posted.fetch_add(1, std::memory_order_release);
-        }
-        cv.notify_one();
-    }
-    void wait()
-    {
-        const int want = posted.load(std::memory_order_acquire);
-        while (finished.load(std::memory_order_acquire) != want) __builtin_ia32_pause();
-    }
-    void stop()
-    {
-        if (!th.joinable()) return;
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            quit = true;
-        }
-        cv.notify_one();
-        th.join();
-    }
 };
 
 struct dbot_multi
@@ -207,6 +144,13 @@ static int multi_destroy(dbot_b200_sensor* s)
 {
     dbot_multi* m = s->multi;
     if (!m) return 0;
+    for (int k = 0; k < DBOT_STAGERS; ++k)
+        if (s->stager[k])
+        {
+            s->stager[k]->stop();
+            delete s->stager[k];
+            s->stager[k] = nullptr;
+        }
     for (int g = 1; g < m->G; ++g)
         if (m->worker[g])
         {
@@ -372,7 +316,21 @@ static int multi_set_observation(dbot_b200_sensor* s, const float* depth_m)
         int rc = multi_sync_all(m);
         if (rc) return rc;
     }
-    memcpy(m->h_obs, depth_m, bytes);
+    {
+        /* staged once for all GPUs, in pieces by this thread and the handle's staging helpers */
+        const size_t total = (size_t)s->kp.rows * s->kp.cols;
+        const int pieces = total >= 65536 ? DBOT_STAGERS + 1 : 1;
+        if (pieces > 1) ensure_stagers(s);
+        for (int piece = 1; piece < pieces; ++piece)
+        {
+            const size_t a = total * piece / pieces, b = total * (piece + 1) / pieces;
+            float* dst = m->h_obs + a;
+            const float* src = depth_m + a;
+            s->stager[piece - 1]->post([dst, src, a, b] { memcpy(dst, src, (b - a) * sizeof(float)); });
+        }
+        memcpy(m->h_obs, depth_m, (total / pieces) * sizeof(float));
+        for (int piece = 1; piece < pieces; ++piece) s->stager[piece - 1]->wait();
+    }
     int shard_rc[DBOT_B200_MAX_DEVICES] = {0};
     std::string shard_err[DBOT_B200_MAX_DEVICES];
     multi_for_each_shard(m, [&](int g) {
