@@ -71,16 +71,22 @@ def resampled_parents(n, rng):
 
 
 def make_inputs(w, render, rank):
-    rng = synth.rng_for(CONFIG_ID, stream=rank)
+    """One scene for the whole job -- the sharded filter tracks ONE object and every rank sees the same depth
+    frames (frame, mesh and camera are replicated) -- and every rank's own particles
+    around it.  (Up to round 2's first 8-GPU run every rank drew its own scene: an object 0.7 m away covers
+    twice the pixels of one 1.0 m away, and the step time was that of the rank with the nearest object.)"""
+    rng = synth.rng_for(CONFIG_ID)
     gt = synth.ground_truth_poses(len(w["V"]), rng)
     frames = [synth.make_frame(render, gt, w["rows"], w["cols"], rng) for _ in range(N_FRAMES)]
+    if rank:
+        rng = synth.rng_for(CONFIG_ID, stream=rank)
     poses = [synth.particle_poses(gt, w["n"], rng) for _ in range(N_FRAMES)]
     parents = [resampled_parents(w["n"], rng) for _ in range(N_FRAMES)]
     return gt, frames, poses, parents
 
 
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region, read through NVML every 2 ms (an
+    """SM clock + throttle reasons DURING the timed region, read through NVML every 5 ms (an
     nvidia-smi process takes longer to start than a timed region lasts); falls back to nvidia-smi."""
 
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
@@ -127,7 +133,7 @@ class ClockSampler:
                 self.samples.append(self.sample())
             except Exception:
                 pass
-            self.stop.wait(0.002 if self.nvml is not None else 0.1)
+            self.stop.wait(0.005 if self.nvml is not None else 0.1)
 
     def __enter__(self):
         self.thread.start()

@@ -66,6 +66,7 @@ class FilterConfig(C.Structure):
 
 
 IPC_HANDLE_BYTES = 64   # DBOT_B200_IPC_HANDLE_BYTES
+OPT_STAGING_THREADS = 1  # DBOT_B200_OPT_STAGING_THREADS
 
 # name -> (restype, argtypes); every symbol include/dbot_b200.h declares
 _P = C.c_void_p
@@ -94,6 +95,7 @@ SIGNATURES = {
     "dbot_b200_loglikes_gather_device": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32]),
     "dbot_b200_peer_gather_result": (_P, [_P]),
     "dbot_b200_shard_scan": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "dbot_b200_set_option": (C.c_int, [_P, C.c_int32, C.c_int64]),
     "dbot_b200_device_count": (C.c_int, [_P]),
     "dbot_b200_migrated_slots": (C.c_int64, [_P]),
     "dbot_b200_n_slots": (C.c_int, [_P]),

@@ -33,6 +33,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -60,6 +61,7 @@
 #define DBOT_COMPUTE_REGS 72
 #endif
 #define DBOT_STAGERS 2             /* host threads beside the caller's that stage a pageable depth frame */
+#define DBOT_STAGE_PIECES 8        /* ... in this many pieces (150 KB each at 640x480) */
 #define DBOT_CHUNK_MAX_VERTS 3072
 #define DBOT_CHUNK_MAX_TRIS 6144
 #define DBOT_FULL 0xffffffffu
@@ -202,8 +204,18 @@ struct dbot_b200_sensor
     int poisoned;            /* an update failed on the device: the slot tables are half-built, reset() required */
     struct dbot_multi* multi; /* != nullptr: this handle shards its particles over several GPUs (multi_device.cuh) */
     struct dbot_peer_gather* peer; /* != nullptr: one rank of a process-per-GPU group (peer_gather.cuh) */
-    dbot_shard_worker* stager[DBOT_STAGERS]; /* helpers that copy thirds of a pageable depth frame into h_obs */
+    dbot_shard_worker* stager[DBOT_STAGERS]; /* helpers that copy pieces of a pageable depth frame into h_obs */
+    dbot_stage_job* stage;
+    int stagers_wanted; /* DBOT_B200_OPT_STAGING_THREADS, 0 .. DBOT_STAGERS */
+    /* DBOT_B200_HOST_TIMING=1: host microseconds spent in the calls of a frame (printed by destroy) */
+    int host_timing;
+    int64_t ht_obs_calls, ht_ll_calls;
+    double ht_us[4]; /* set_observation (pageable) | loglikes: stage + enqueue | loglikes: wait + copy out | spare */
 };
+static double host_now_us()
+{
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 #define DBOT_CHECK_USABLE(s, what)                                                                          \
     do                                                                                                      \
     {                                                                                                       \
@@ -226,6 +238,7 @@ static dbot_b200_sensor* multi_child(dbot_b200_sensor* s, int g);
 static int multi_count(dbot_b200_sensor* s);
 /* peer_gather.cuh */
 static void peer_gather_close(dbot_b200_sensor* s);
+static void stop_stagers(dbot_b200_sensor* s);
 #define DBOT_SINGLE_ONLY(s, what)                                                                      \
     do                                                                                                 \
     {                                                                                                  \
@@ -408,13 +421,13 @@ extern "C" int dbot_b200_destroy(dbot_b200_sensor* s)
     }
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->host_timing && s->ht_ll_calls > 0)
+        fprintf(stderr, "dbot_b200 host timing, device %d: set_observation (pageable) %.1f us x %lld, loglikes stage + "
+                        "enqueue %.1f us, wait + copy out %.1f us x %lld\n", s->device,
+                s->ht_us[0] / (double)std::max<int64_t>(s->ht_obs_calls, 1), (long long)s->ht_obs_calls,
+                s->ht_us[1] / (double)s->ht_ll_calls, s->ht_us[2] / (double)s->ht_ll_calls, (long long)s->ht_ll_calls);
     peer_gather_close(s);
-    for (int k = 0; k < DBOT_STAGERS; ++k)
-        if (s->stager[k])
-        {
-            s->stager[k]->stop();
-            delete s->stager[k];
-        }
+    stop_stagers(s);
     cudaFree(s->d_mesh); cudaFree(s->d_chunks); cudaFree(s->d_obs); cudaFree(s->d_tab);
     cudaFree(s->d_pool); cudaFree(s->d_loc[0]); cudaFree(s->d_loc[1]); cudaFree(s->d_free);
     cudaFree(s->d_free_count); cudaFree(s->d_cnt); cudaFree(s->d_last); cudaFree(s->d_pending);
@@ -443,6 +456,11 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     if (device_id < 0 || device_id >= n_dev)
         return fail(-2, "device_id %d out of range (have %d)", device_id, n_dev);
     s->device = device_id;
+    s->stagers_wanted = DBOT_STAGERS;
+    {
+        const char* t = getenv("DBOT_B200_HOST_TIMING");
+        s->host_timing = t && *t == '1';
+    }
     CUDA_TRY(cudaSetDevice(s->device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
@@ -692,14 +710,51 @@ static int launch_observation(dbot_b200_sensor* s, const float* d_depth)
 /* the helpers that stage pageable depth frames are started with the first such frame */
 static void ensure_stagers(dbot_b200_sensor* s)
 {
-    if (s->stager[0]) return;
-    for (int k = 0; k < DBOT_STAGERS; ++k)
+    if (s->stage) return;
+    s->stage = new dbot_stage_job();
+    for (int k = 0; k < s->stagers_wanted; ++k)
     {
         dbot_shard_worker* w = new dbot_shard_worker();
         w->spin = 4000; /* frames are a third of a millisecond apart at best: sleep between them */
         w->th = std::thread([w] { w->loop(-1); });
         s->stager[k] = w;
     }
+}
+static void stop_stagers(dbot_b200_sensor* s)
+{
+    for (int k = 0; k < DBOT_STAGERS; ++k)
+        if (s->stager[k])
+        {
+            s->stager[k]->stop();
+            delete s->stager[k];
+            s->stager[k] = nullptr;
+        }
+    delete s->stage;
+    s->stage = nullptr;
+}
+/* arm the staging job for one frame and wake the helpers; the caller then claims pieces itself */
+static dbot_stage_job* begin_staging(dbot_b200_sensor* s, float* dst, const float* src, size_t count)
+{
+    ensure_stagers(s);
+    dbot_stage_job* job = s->stage;
+    job->arm(dst, src, count * sizeof(float), count >= 65536 ? DBOT_STAGE_PIECES : 1);
+    if (job->np > 1)
+        for (int k = 0; k < DBOT_STAGERS; ++k)
+            if (s->stager[k]) s->stager[k]->post([job] { job->help(); });
+    return job;
+}
+
+extern "C" int dbot_b200_set_option(dbot_b200_sensor* s, int32_t option, int64_t value)
+{
+    if (!s) return fail(-1, "set_option: null handle");
+    if (option == DBOT_B200_OPT_STAGING_THREADS)
+    {
+        if (value < 0 || value > DBOT_STAGERS) return fail(-2, "set_option: staging threads must be 0 .. %d", DBOT_STAGERS);
+        stop_stagers(s); /* restarted with the next pageable frame */
+        s->stagers_wanted = (int)value;
+        return 0;
+    }
+    return fail(-2, "set_option: unknown option %d", option);
 }
 
 static bool is_pinned_host(const void* p)
@@ -733,34 +788,35 @@ extern "C" int dbot_b200_set_observation(dbot_b200_sensor* s, const float* depth
     /* pageable: stage in the handle's own pinned buffer; the copy and the table kernel are left
      * running -- every later call on this handle is ordered behind them on the same stream, and the
      * staging buffer is not touched again before they are done */
+    const double ht0 = s->host_timing ? host_now_us() : 0.0;
     if (s->obs_in_flight) CUDA_TRY(cudaEventSynchronize(s->ev_obs));
-    /* in pieces: the helpers stage theirs while this thread stages the first, and the copy engine moves a piece
-     * while the next one is still being staged */
-    const size_t total = (size_t)s->kp.rows * s->kp.cols;
-    const int pieces = total >= 65536 ? DBOT_STAGERS + 1 : 1;
-    if (pieces > 1) ensure_stagers(s);
-    for (int piece = 1; piece < pieces; ++piece)
-    {
-        const size_t a = total * piece / pieces, b = total * (piece + 1) / pieces;
-        float* dst = s->h_obs + a;
-        const float* src = depth_m + a;
-        s->stager[piece - 1]->post([dst, src, a, b] { memcpy(dst, src, (b - a) * sizeof(float)); });
-    }
+    /* in pieces that this thread and the staging helpers claim one by one; every piece goes to the device as soon
+     * as it and all pieces before it are staged, so the copy engine works while the rest is still being staged */
+    dbot_stage_job* job = begin_staging(s, s->h_obs, depth_m, (size_t)s->kp.rows * s->kp.cols);
     cudaError_t copy_err = cudaSuccess;
-    for (int piece = 0; piece < pieces; ++piece)
+    for (int issued = 0; issued < job->np;)
     {
-        const size_t a = total * piece / pieces, b = total * (piece + 1) / pieces;
-        if (piece == 0)
-            memcpy(s->h_obs + a, depth_m + a, (b - a) * sizeof(float));
-        else
-            s->stager[piece - 1]->wait(); /* always: no job may outlive this call (it reads the caller's buffer) */
-        if (copy_err == cudaSuccess)
-            copy_err = cudaMemcpyAsync(s->d_obs + a, s->h_obs + a, (b - a) * sizeof(float), cudaMemcpyHostToDevice, s->stream);
+        const bool mine = job->claim_one();
+        while (issued < job->np && job->is_done(issued))
+        {
+            const size_t a = job->cut(issued), b = job->cut(issued + 1);
+            if (copy_err == cudaSuccess)
+                copy_err = cudaMemcpyAsync((char*)s->d_obs + a, (const char*)s->h_obs + a, b - a, cudaMemcpyHostToDevice,
+                                           s->stream);
+            ++issued;
+        }
+        if (!mine && issued < job->np) __builtin_ia32_pause(); /* a helper is still copying a piece it claimed */
     }
     CUDA_TRY(copy_err);
     CUDA_TRY(cudaEventRecord(s->ev_obs, s->stream));
     s->obs_in_flight = 1;
-    return launch_observation(s, s->d_obs);
+    const int orc = launch_observation(s, s->d_obs);
+    if (s->host_timing)
+    {
+        s->ht_us[0] += host_now_us() - ht0;
+        s->ht_obs_calls++;
+    }
+    return orc;
 }
 
 extern "C" int dbot_b200_set_observation_device(dbot_b200_sensor* s, const float* d_depth_m)
@@ -956,10 +1012,18 @@ extern "C" int dbot_b200_loglikes(dbot_b200_sensor* s, const float* poses, int32
             return fail(-7, "loglikes: indices[%d]=%d is not an occlusion slot (have %d)", i,
                         indices[i], s->n_slots);
     if (n == 0) return 0; /* as dbot's model: a call without particles changes nothing, update or not */
+    const double ht0 = s->host_timing ? host_now_us() : 0.0;
     int rc = loglikes_enqueue(s, poses, indices, n, update);
     if (rc) return rc;
+    const double ht1 = s->host_timing ? host_now_us() : 0.0;
     rc = loglikes_finish(s, n, update, out_loglikes);
     if (rc) return rc;
+    if (s->host_timing)
+    {
+        s->ht_us[1] += ht1 - ht0;
+        s->ht_us[2] += host_now_us() - ht1;
+        s->ht_ll_calls++;
+    }
     if (update)
         for (int i = 0; i < n; ++i) indices[i] = i;
     return 0;

@@ -69,3 +69,44 @@ struct dbot_shard_worker
     }
 };
 
+
+/* A pageable buffer copied into a page-locked one in pieces that ANY thread may claim: the caller arms the job,
+ * wakes the helpers and starts claiming pieces itself.  Helpers that wake promptly take their share; one that
+ * wakes late (a sleeping thread can take a quarter of a millisecond to get a core on a busy host) finds nothing
+ * left and costs nothing -- the caller never waits for a helper that has not claimed anything.  The job lives in
+ * the handle, not on the stack: a late helper may look at it after the call has returned (it then sees every piece
+ * taken, or already helps with the next frame). */
+struct dbot_stage_job
+{
+    static constexpr int MAX_PIECES = 16;
+    std::atomic<int> next{MAX_PIECES};
+    std::atomic<int> done[MAX_PIECES];
+    char* dst = nullptr;
+    const char* src = nullptr;
+    size_t bytes = 0;
+    int np = 0;
+
+    size_t cut(int i) const { return i >= np ? bytes : (bytes / 64 * (size_t)i / (size_t)np) * 64; }
+    void arm(void* d, const void* s, size_t n, int pieces)
+    {
+        dst = (char*)d;
+        src = (const char*)s;
+        bytes = n;
+        np = pieces;
+        for (int i = 0; i < pieces; ++i) done[i].store(0, std::memory_order_relaxed);
+        next.store(0, std::memory_order_release);
+    }
+    bool claim_one()
+    {
+        const int i = next.fetch_add(1, std::memory_order_acq_rel);
+        if (i < 0 || i >= np) return false;
+        memcpy(dst + cut(i), src + cut(i), cut(i + 1) - cut(i));
+        done[i].store(1, std::memory_order_release);
+        return true;
+    }
+    void help()
+    {
+        while (claim_one()) {}
+    }
+    bool is_done(int i) const { return done[i].load(std::memory_order_acquire) != 0; }
+};

@@ -27,6 +27,7 @@
 #pragma once
 #include <dlfcn.h>
 
+#include <chrono>
 #include <thread>
 
 /* the handful of NCCL declarations this file needs (bound with dlsym; nccl.h is not required to build) */
@@ -63,6 +64,7 @@ struct dbot_multi
     float* h_obs;
     int obs_in_flight;
     cudaEvent_t ev_done[DBOT_B200_MAX_DEVICES], ev_begin[DBOT_B200_MAX_DEVICES], ev_end[DBOT_B200_MAX_DEVICES];
+    cudaEvent_t ev_frame; /* the depth frame has landed in the first GPU's memory */
     /* NCCL */
     void* nccl_lib;
     pfn_ncclCommInitAll CommInitAll;
@@ -80,6 +82,28 @@ struct dbot_multi
     int64_t migrated;
     std::vector<int32_t>* local_idx;
     dbot_shard_worker* worker[DBOT_B200_MAX_DEVICES]; /* [0] unused: shard 0 runs on the caller's thread */
+    /* DBOT_B200_HOST_TIMING=1: where the host time of a frame goes (printed by destroy) */
+    int timing;
+    int64_t timed_calls;
+    double phase_us[8];
+    cudaEvent_t tev[DBOT_B200_MAX_DEVICES][4]; /* frame in / table done / particle launch / particle kernel done */
+    double gpu_us[DBOT_B200_MAX_DEVICES][3];
+};
+static const char* const dbot_multi_phase_names[8] = {"obs: stage frame", "obs: enqueue on all shards", "loglikes: check + localise parents",
+                                                      "loglikes: enqueue on all shards", "loglikes: gather set-up",
+                                                      "loglikes: wait for all shards", "loglikes: copy out", ""};
+struct dbot_phase_clock
+{
+    dbot_multi* m;
+    std::chrono::steady_clock::time_point t;
+    explicit dbot_phase_clock(dbot_multi* mm) : m(mm), t(std::chrono::steady_clock::now()) {}
+    void mark(int phase)
+    {
+        if (!m->timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        m->phase_us[phase] += std::chrono::duration<double, std::micro>(now - t).count();
+        t = now;
+    }
 };
 
 /* run fn(g) for every shard: shard 0 on this thread, the others on their workers; returns when all are done */
@@ -144,13 +168,18 @@ static int multi_destroy(dbot_b200_sensor* s)
 {
     dbot_multi* m = s->multi;
     if (!m) return 0;
-    for (int k = 0; k < DBOT_STAGERS; ++k)
-        if (s->stager[k])
-        {
-            s->stager[k]->stop();
-            delete s->stager[k];
-            s->stager[k] = nullptr;
-        }
+    if (m->timing && m->timed_calls > 0)
+    {
+        fprintf(stderr, "dbot_b200 host timing, %d GPUs, %lld loglikes calls, microseconds per call:\n", m->G,
+                (long long)m->timed_calls);
+        for (int k = 0; k < 7; ++k)
+            fprintf(stderr, "  %-40s %9.1f\n", dbot_multi_phase_names[k], m->phase_us[k] / (double)m->timed_calls);
+        for (int g = 0; g < m->G; ++g)
+            fprintf(stderr, "  GPU %d stream: frame in + table %8.1f   idle until the particle launch %8.1f   poses + plan + "
+                            "particle kernel %8.1f\n", m->dev[g], m->gpu_us[g][0] / (double)m->timed_calls,
+                    m->gpu_us[g][1] / (double)m->timed_calls, m->gpu_us[g][2] / (double)m->timed_calls);
+    }
+    stop_stagers(s);
     for (int g = 1; g < m->G; ++g)
         if (m->worker[g])
         {
@@ -172,6 +201,7 @@ static int multi_destroy(dbot_b200_sensor* s)
         delete m->imported[g];
         dbot_b200_destroy(m->child[g]);
     }
+    if (m->ev_frame) cudaEventDestroy(m->ev_frame);
     cudaFreeHost(m->h_all);
     cudaFreeHost(m->h_obs);
     delete m->local_idx;
@@ -222,6 +252,11 @@ static int multi_create(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     m->gather_mode = cfg->gather_mode;
     m->cnt_max = (cfg->max_particles + G - 1) / G;
     m->local_idx = new std::vector<int32_t>();
+    s->stagers_wanted = DBOT_STAGERS;
+    {
+        const char* t = getenv("DBOT_B200_HOST_TIMING");
+        m->timing = t && *t == '1';
+    }
     for (int g = 0; g < G; ++g)
     {
         m->dev[g] = cfg->device_ids ? cfg->device_ids[g] : g;
@@ -250,6 +285,8 @@ static int multi_create(const dbot_b200_config* cfg, dbot_b200_sensor* s)
         CUDA_TRY(cudaEventCreateWithFlags(&m->ev_done[g], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreate(&m->ev_begin[g]));
         CUDA_TRY(cudaEventCreate(&m->ev_end[g]));
+        if (m->timing)
+            for (int e = 0; e < 4; ++e) CUDA_TRY(cudaEventCreate(&m->tev[g][e]));
     }
     /* every shard reads the others' pools (slot migration) and, in fused mode, writes their gathered vectors */
     for (int g = 0; g < G; ++g)
@@ -266,6 +303,8 @@ static int multi_create(const dbot_b200_config* cfg, dbot_b200_sensor* s)
             else if (e != cudaSuccess)
                 return fail((int)e, "cudaDeviceEnablePeerAccess(%d -> %d): %s", m->dev[g], m->dev[h], cudaGetErrorString(e));
         }
+    CUDA_TRY(cudaSetDevice(m->dev[0]));
+    CUDA_TRY(cudaEventCreateWithFlags(&m->ev_frame, cudaEventDisableTiming));
     CUDA_TRY(cudaHostAlloc(&m->h_all, (size_t)G * m->cnt_max * sizeof(double), cudaHostAllocPortable));
     CUDA_TRY(cudaHostAlloc(&m->h_obs, (size_t)cfg->rows * cfg->cols * sizeof(float), cudaHostAllocPortable));
     if (m->gather_mode == 0)
@@ -310,39 +349,62 @@ static int multi_reset(dbot_b200_sensor* s)
 static int multi_set_observation(dbot_b200_sensor* s, const float* depth_m)
 {
     dbot_multi* m = s->multi;
-    const size_t bytes = (size_t)s->kp.rows * s->kp.cols * sizeof(float);
     if (m->obs_in_flight)
     {
+        /* the staging buffer and the first GPU's frame buffer may still be read */
         int rc = multi_sync_all(m);
         if (rc) return rc;
     }
-    {
-        /* staged once for all GPUs, in pieces by this thread and the handle's staging helpers */
-        const size_t total = (size_t)s->kp.rows * s->kp.cols;
-        const int pieces = total >= 65536 ? DBOT_STAGERS + 1 : 1;
-        if (pieces > 1) ensure_stagers(s);
-        for (int piece = 1; piece < pieces; ++piece)
+    dbot_phase_clock clk(m);
+    /* The frame crosses PCIe ONCE, to the first GPU -- staged in pieces that this thread and the staging helpers
+     * claim, every piece on its way as soon as it and the pieces before it are staged.  The other GPUs do not
+     * upload their own copy (measured on an 8-GPU box: eight uploads of the same page-locked buffer take 0.5 ms,
+     * they run one after the other): their table kernels read the raw frame out of the first GPU's memory over
+     * NVLink (peer loads, 1.2 MB each) once its copy has landed. */
+    dbot_b200_sensor* c0 = m->child[0];
+    CUDA_TRY(cudaSetDevice(m->dev[0]));
+    if (m->timing)
+        for (int g = 0; g < m->G; ++g)
         {
-            const size_t a = total * piece / pieces, b = total * (piece + 1) / pieces;
-            float* dst = m->h_obs + a;
-            const float* src = depth_m + a;
-            s->stager[piece - 1]->post([dst, src, a, b] { memcpy(dst, src, (b - a) * sizeof(float)); });
+            CUDA_TRY(cudaSetDevice(m->dev[g]));
+            CUDA_TRY(cudaEventRecord(m->tev[g][0], m->child[g]->stream));
         }
-        memcpy(m->h_obs, depth_m, (total / pieces) * sizeof(float));
-        for (int piece = 1; piece < pieces; ++piece) s->stager[piece - 1]->wait();
+    CUDA_TRY(cudaSetDevice(m->dev[0]));
+    {
+        dbot_stage_job* job = begin_staging(s, m->h_obs, depth_m, (size_t)s->kp.rows * s->kp.cols);
+        cudaError_t copy_err = cudaSuccess;
+        for (int issued = 0; issued < job->np;)
+        {
+            const bool mine = job->claim_one();
+            while (issued < job->np && job->is_done(issued))
+            {
+                const size_t a = job->cut(issued), b = job->cut(issued + 1);
+                if (copy_err == cudaSuccess)
+                    copy_err = cudaMemcpyAsync((char*)c0->d_obs + a, (const char*)m->h_obs + a, b - a,
+                                               cudaMemcpyHostToDevice, c0->stream);
+                ++issued;
+            }
+            if (!mine && issued < job->np) __builtin_ia32_pause(); /* a helper is still copying a piece it claimed */
+        }
+        CUDA_TRY(copy_err);
     }
+    CUDA_TRY(cudaEventRecord(m->ev_frame, c0->stream));
+    clk.mark(0);
     int shard_rc[DBOT_B200_MAX_DEVICES] = {0};
     std::string shard_err[DBOT_B200_MAX_DEVICES];
     multi_for_each_shard(m, [&](int g) {
         dbot_b200_sensor* c = m->child[g];
         auto body = [&]() -> int {
             CUDA_TRY(cudaSetDevice(m->dev[g]));
-            CUDA_TRY(cudaMemcpyAsync(c->d_obs, m->h_obs, bytes, cudaMemcpyHostToDevice, c->stream));
-            return launch_observation(c, c->d_obs);
+            if (g > 0) CUDA_TRY(cudaStreamWaitEvent(c->stream, m->ev_frame, 0));
+            const int orc = launch_observation(c, c0->d_obs);
+            if (m->timing) CUDA_TRY(cudaEventRecord(m->tev[g][1], c->stream));
+            return orc;
         };
         shard_rc[g] = body();
         if (shard_rc[g]) shard_err[g] = g_last_error; /* thread-local: carried back to the caller's thread */
     });
+    clk.mark(1);
     m->obs_in_flight = 1;
     for (int g = 0; g < m->G; ++g)
         if (shard_rc[g])
@@ -426,12 +488,14 @@ static int multi_loglikes(dbot_b200_sensor* s, const float* poses, int32_t* indi
 {
     dbot_multi* m = s->multi;
     const int G = m->G;
+    dbot_phase_clock clk(m);
     for (int i = 0; i < n; ++i)
         if (indices[i] < 0 || indices[i] >= m->n_slots)
             return fail(-7, "loglikes: indices[%d]=%d is not an occlusion slot (have %d)", i, indices[i], m->n_slots);
     if (n == 0) return 0;
     int rc = multi_localise_parents(s, indices, n);
     if (rc) return rc;
+    clk.mark(2);
     const int32_t* local = m->local_idx->data();
     const size_t pose_stride = (size_t)12 * s->kp.n_obj;
     int cnt = (n + G - 1) / G;
@@ -454,12 +518,16 @@ static int multi_loglikes(dbot_b200_sensor* s, const float* poses, int32_t* indi
                 c->kp.out_offset = g * cnt;
                 for (int h = 0; h < G; ++h) c->kp.peer_out[h] = m->d_all[h];
             }
-            return loglikes_enqueue(c, poses + (size_t)lo * pose_stride, local + lo, hi - lo, update);
+            if (m->timing) CUDA_TRY(cudaEventRecord(m->tev[g][2], c->stream));
+            const int erc = loglikes_enqueue(c, poses + (size_t)lo * pose_stride, local + lo, hi - lo, update);
+            if (m->timing) CUDA_TRY(cudaEventRecord(m->tev[g][3], c->stream));
+            return erc;
         };
         shard_rc[g] = body();
         if (shard_rc[g]) shard_err[g] = g_last_error; /* thread-local: carried back to the caller's thread */
     };
     multi_for_each_shard(m, enqueue_shard);
+    clk.mark(3);
     for (int g = 0; g < G; ++g)
         if (shard_rc[g])
         {
@@ -491,12 +559,23 @@ static int multi_loglikes(dbot_b200_sensor* s, const float* poses, int32_t* indi
     CUDA_TRY(cudaSetDevice(m->dev[0]));
     CUDA_TRY(cudaMemcpyAsync(m->h_all, m->d_all[0], (size_t)G * cnt * sizeof(double), cudaMemcpyDeviceToHost,
                              m->child[0]->stream));
+    clk.mark(4);
     int first_error = 0;
     std::string first_text;
     multi_for_each_shard(m, [&](int g) { /* error flags back, wait: every shard on its own thread */
         shard_rc[g] = loglikes_finish(m->child[g], 0, update, nullptr);
         if (shard_rc[g]) shard_err[g] = g_last_error;
     });
+    clk.mark(5);
+    if (m->timing && m->obs_in_flight)
+        for (int g = 0; g < G; ++g)
+            for (int e = 0; e < 3; ++e)
+            {
+                float ms = 0.f;
+                cudaSetDevice(m->dev[g]);
+                if (cudaEventElapsedTime(&ms, m->tev[g][e], m->tev[g][e + 1]) == cudaSuccess) m->gpu_us[g][e] += 1e3 * ms;
+                else cudaGetLastError();
+            }
     for (int g = 0; g < G; ++g)
         if (shard_rc[g] && !first_error)
         {
@@ -524,6 +603,8 @@ static int multi_loglikes(dbot_b200_sensor* s, const float* poses, int32_t* indi
         m->fresh = 0;
         for (int g = 0; g < G; ++g) m->imported[g]->clear();
     }
+    clk.mark(6);
+    m->timed_calls += m->timing;
     return 0;
 }
 

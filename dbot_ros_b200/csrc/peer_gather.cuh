@@ -217,6 +217,7 @@ extern "C" int dbot_b200_loglikes_gather(dbot_b200_sensor* s, const float* poses
             return fail(-7, "loglikes_gather: indices[%d]=%d is not an occlusion slot of this rank (have %d)", i,
                         indices_local[i], s->n_slots);
     CUDA_TRY(cudaSetDevice(s->device));
+    const double ht0 = s->host_timing ? host_now_us() : 0.0;
     if (n_local > 0)
     {
         const size_t pose_bytes = (size_t)n_local * 12 * s->kp.n_obj * sizeof(float);
@@ -230,10 +231,17 @@ extern "C" int dbot_b200_loglikes_gather(dbot_b200_sensor* s, const float* poses
     if (rc) return rc;
     const size_t bytes = (size_t)pg->world * width * sizeof(double);
     CUDA_TRY(cudaMemcpyAsync(pg->h_all, dbot_b200_peer_gather_result(s), bytes, cudaMemcpyDeviceToHost, s->stream));
+    const double ht1 = s->host_timing ? host_now_us() : 0.0;
     rc = loglikes_finish(s, 0, update, nullptr);
     s->obs_in_flight = 0;
     if (rc) return rc;
     memcpy(out_all, pg->h_all, bytes);
+    if (s->host_timing)
+    {
+        s->ht_us[1] += ht1 - ht0;
+        s->ht_us[2] += host_now_us() - ht1;
+        s->ht_ll_calls++;
+    }
     return 0;
 }
 

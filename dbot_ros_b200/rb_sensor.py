@@ -357,6 +357,10 @@ class B200KinectImageModel(RbSensor):
             self._h, C.c_void_p(d_poses_ptr), C.c_void_p(d_indices_ptr), int(n_local), 1 if update else 0,
             C.c_void_p(d_out_ptr), int(width)))
 
+    def set_staging_threads(self, n):
+        """host threads that help to stage pageable depth frames (default 2; 0 = the caller's thread alone)"""
+        abi.check(self._lib, self._lib.dbot_b200_set_option(self._h, abi.OPT_STAGING_THREADS, int(n)))
+
     @property
     def peer_gather_result(self):
         """device pointer of the gathered vector the last gathering call filled"""

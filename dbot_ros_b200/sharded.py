@@ -84,6 +84,10 @@ class ShardedRbSensor(RbSensor):
         from .rb_sensor import _LIVE_WRAPPERS
 
         _LIVE_WRAPPERS.add(self)
+        if self.world > 1 and hasattr(self.local, "set_staging_threads"):
+            # ranks run in lock step (every call ends in a gather): a helper thread that gets a core late on ONE
+            # rank holds up all of them, so every rank stages its depth frames on the calling thread alone
+            self.local.set_staging_threads(0)
         self.gather = "collective"   # or "fused": peer stores from the particle kernel (csrc/peer_gather.cuh)
         self.gather_reason = None
         self._connect_peers()

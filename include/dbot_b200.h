@@ -203,6 +203,13 @@ int dbot_b200_free_slot_count(dbot_b200_sensor* s);
 /* occlusion probability image of one slot as of the current observation time, rows*cols floats */
 int dbot_b200_get_occlusion(dbot_b200_sensor* s, int32_t slot, float* out_occ);
 
+/* ---- tuning ---- */
+/* host threads beside the caller's that help to stage a pageable depth frame into page-locked memory (default 2;
+ * 0: the caller's thread stages alone).  Helpers take a third off a single tracker's frame time; ranks of a
+ * process-per-GPU group run in lock step, where every extra thread is a source of stragglers: sharded.py sets 0. */
+#define DBOT_B200_OPT_STAGING_THREADS 1
+int dbot_b200_set_option(dbot_b200_sensor* s, int32_t option, int64_t value);
+
 /* ---- measurement hooks (bench.py) ---- */
 /* CUDA events on the handle's stream: begin records, end records + synchronises and returns ms */
 int dbot_b200_timer_begin(dbot_b200_sensor* s);
