@@ -84,9 +84,10 @@ class ShardedRbSensor(RbSensor):
         from .rb_sensor import _LIVE_WRAPPERS
 
         _LIVE_WRAPPERS.add(self)
-        if self.world > 1 and hasattr(self.local, "set_staging_threads"):
+        if self.world > 2 and hasattr(self.local, "set_staging_threads"):
             # ranks run in lock step (every call ends in a gather): a helper thread that gets a core late on ONE
-            # rank holds up all of them, so every rank stages its depth frames on the calling thread alone
+            # rank holds up all of them.  Measured end to end: helpers +10 % with 2 ranks, +-0 with 4, -20 % with
+            # 8 -- beyond two ranks every rank stages its depth frames on the calling thread alone
             self.local.set_staging_threads(0)
         self.gather = "collective"   # or "fused": peer stores from the particle kernel (csrc/peer_gather.cuh)
         self.gather_reason = None
@@ -377,11 +378,21 @@ class ShardedRbSensor(RbSensor):
                 raise IndexError("loglikes: parent slot out of range (have %d)" % self.n_slots)
             if rc == 1:
                 self.migrate(indices, n)
+            all_local = rc == 0 and not self._imported_local
         else:
             if np.any(indices < 0) or np.any(indices >= self.n_slots):
                 raise IndexError("loglikes: parent slot out of range (have %d)" % self.n_slots)
             self.migrate(indices, n)
-        lo, hi, local_idx = self.local_parents(indices, n)
+            all_local = False
+        if all_local:
+            # the common case, without the general path's bookkeeping: this rank's parents are its own slots
+            lo, hi = shard_bounds(n, self.world, self.rank)
+            if self.n_slots == 1:
+                local_idx = np.zeros(hi - lo, dtype=np.int32)
+            else:
+                local_idx = indices[lo:hi] - np.int32(shard_bounds(self.n_slots, self.world, self.rank)[0])
+        else:
+            lo, hi, local_idx = self.local_parents(indices, n)
         if self.gather == "fused":
             out = self._evaluate_and_gather_fused(poses, lo, hi, local_idx, n, update)
         elif self.device.type == "cuda" and hasattr(self.local, "loglikes_device"):
