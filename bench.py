@@ -464,11 +464,10 @@ def main():
     copies = float(np.mean([len(p) - len(np.unique(p)) for p in parents]))
     sample = poses[0][:: max(1, n // 16)][:16]
     n_cov = float(np.mean([np.isfinite(sensor.render(q)).sum() for q in sample]))
-    # a copy moves the rows in which the parent's image can differ from the background (dbot_b200_slot_rows)
-    band = [sensor.slot_rows(sl) for sl in range(0, n, max(1, n // 32))]
-    band_rows = float(np.mean([max(0, b - a + 1) for a, b in band]))
-    pitch = (cols + 7) // 8 * 8
-    alg_bytes = copies * 8.0 * pitch * band_rows + n * 8.0 * n_cov
+    # a copy moves the rectangle in which the parent's image can differ from the background (dbot_b200_slot_rect)
+    rects = [sensor.slot_rect(sl) for sl in range(0, n, max(1, n // 32))]
+    rect_px = float(np.mean([max(0, r1 - r0 + 1) * max(0, c1 - c0 + 1) for r0, r1, c0, c1 in rects]))
+    alg_bytes = copies * 8.0 * rect_px + n * 8.0 * n_cov
     dense_bytes = 8.0 * P * n                     # SURVEY.md 8(d), dense formulation: 4P read + 4P written per particle
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
     frac_dram = (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic else None
@@ -483,8 +482,8 @@ def main():
                                   "launch of the same workload)" if traffic else None,
                 "issue_active_pct_ncu": issue_pct,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "algorithmic_bytes": "copying children (%.0f of %d) x 8 B x %d px/row x %.0f touched rows + %d covered "
-                                     "pixels x 8 B x %d particles" % (copies, n, pitch, band_rows, round(n_cov), n),
+                "algorithmic_bytes": "copying children (%.0f of %d) x 8 B x %.0f px of the parent's touched rectangle + "
+                                     "%d covered pixels x 8 B x %d particles" % (copies, n, rect_px, round(n_cov), n),
                 "dense_equivalent": {"bytes_per_launch": dense_bytes, "GBps": dense_bytes / (avg_ms * 1e-3) / 1e9,
                                      "frac": dense_bytes / (avg_ms * 1e-3) / 1e9 / peak,
                                      "note": "8P per particle whether copied or not (SURVEY.md 8d); not a DRAM rate"},

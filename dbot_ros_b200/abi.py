@@ -102,6 +102,7 @@ SIGNATURES = {
     "dbot_b200_cull_sign": (C.c_int, [_P, C.c_int32]),
     "dbot_b200_observation_time": (C.c_double, [_P]),
     "dbot_b200_slot_rows": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "dbot_b200_slot_rect": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32)]),
     "dbot_b200_free_slot_count": (C.c_int, [_P]),
     "dbot_b200_get_occlusion": (C.c_int, [_P, C.c_int32, _P]),
     "dbot_b200_timer_begin": (C.c_int, [_P]),

@@ -57,7 +57,7 @@
 #define DBOT_PREFETCH_AHEAD 8      /* chunks of DBOT_ST x DBOT_STREAM_UNROLL x 32 B (16 KB) */
 #endif
 #ifndef DBOT_STREAM_REGS
-#define DBOT_STREAM_REGS 56
+#define DBOT_STREAM_REGS 64
 #define DBOT_COMPUTE_REGS 72
 #endif
 #define DBOT_STAGERS 2             /* host threads beside the caller's that stage a pageable depth frame */
@@ -99,9 +99,10 @@ struct dbot_kparams
     const int4* plan;       /* update: per particle { source slot, destination slot, parent, 0 } (physical) */
     const int32_t* order;   /* update: processing order, copying children before adopting ones */
     int32_t* pending;       /* update: per parent, copies of its image still to be read */
-    int2* slot_rows;        /* [2 * max_particles] per PHYSICAL slot: first and last image row that may differ from
-                               the background value (empty: first > last).  Every stored image equals the
-                               background outside these rows, so a copy moves only the parent's rows. */
+    int4* slot_rect;        /* [2 * max_particles] per PHYSICAL slot: { first row, last row, first word, last word } of the
+                               rectangle in which the image may differ from the background value (words = columns
+                               / 8, the 256-bit units of the copy; empty: first > last).  Every stored image equals
+                               the background outside it, so a copy moves only the parent's rectangle. */
     float background;       /* stored value of a never-updated pixel (lazy encoding: constant between rebases) */
     size_t slot_stride;     /* rows*pitch */
     float post_b, post_inv_a; /* update: the posterior o is stored as (o - post_b) * post_inv_a */
@@ -167,7 +168,7 @@ struct dbot_b200_sensor
     int32_t* d_free;        /* stack of unused physical slots + its height */
     int32_t* d_free_count;
     int32_t *d_cnt, *d_last, *d_pending, *d_order;
-    int2* d_slot_rows;      /* touched row range of every physical slot */
+    int4* d_slot_rect;      /* touched rectangle of every physical slot */
     double background;      /* stored value of untouched pixels */
     int4* d_plan;
     float* d_poses;
@@ -431,7 +432,7 @@ extern "C" int dbot_b200_destroy(dbot_b200_sensor* s)
     cudaFree(s->d_mesh); cudaFree(s->d_chunks); cudaFree(s->d_obs); cudaFree(s->d_tab);
     cudaFree(s->d_pool); cudaFree(s->d_loc[0]); cudaFree(s->d_loc[1]); cudaFree(s->d_free);
     cudaFree(s->d_free_count); cudaFree(s->d_cnt); cudaFree(s->d_last); cudaFree(s->d_pending);
-    cudaFree(s->d_order); cudaFree(s->d_plan); cudaFree(s->d_slot_rows); cudaFree(s->d_poses); cudaFree(s->d_indices);
+    cudaFree(s->d_order); cudaFree(s->d_plan); cudaFree(s->d_slot_rect); cudaFree(s->d_poses); cudaFree(s->d_indices);
     cudaFree(s->d_out); cudaFree(s->d_depth); cudaFree(s->d_err);
     cudaFreeHost(s->h_poses); cudaFreeHost(s->h_indices); cudaFreeHost(s->h_out);
     cudaFreeHost(s->h_obs); cudaFreeHost(s->h_depth); cudaFreeHost(s->h_err);
@@ -565,7 +566,7 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     CUDA_TRY(cudaMalloc(&s->d_last, 2 * np * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&s->d_pending, 2 * np * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&s->d_order, np * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&s->d_slot_rows, 2 * np * sizeof(int2)));
+    CUDA_TRY(cudaMalloc(&s->d_slot_rect, 2 * np * sizeof(int4)));
     CUDA_TRY(cudaMalloc(&s->d_plan, np * sizeof(int4)));
     CUDA_TRY(cudaMalloc(&s->d_poses, np * 12 * kp.n_obj * sizeof(float)));
     CUDA_TRY(cudaMalloc(&s->d_indices, np * sizeof(int32_t)));
@@ -645,8 +646,8 @@ static void prof_end(dbot_b200_sensor* s, int which)
 
 /* RbSensor::reset: one logical slot (physical slot 0) at initial_occlusion_prob,
  * every other physical slot free */
-__global__ void dbot_reset_slots_kernel(int32_t* loc, int32_t* free_stack, int32_t* free_count, int2* slot_rows,
-                                        int n_phys, int rows)
+__global__ void dbot_reset_slots_kernel(int32_t* loc, int32_t* free_stack, int32_t* free_count, int4* slot_rect,
+                                        int n_phys, int rows, int row8)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0)
@@ -655,7 +656,7 @@ __global__ void dbot_reset_slots_kernel(int32_t* loc, int32_t* free_stack, int32
         *free_count = n_phys - 1;
     }
     if (i < n_phys - 1) free_stack[i] = n_phys - 1 - i; /* top of the stack = slot 1 */
-    if (i < n_phys) slot_rows[i] = make_int2(rows, -1);  /* every slot holds the background everywhere */
+    if (i < n_phys) slot_rect[i] = make_int4(rows, -1, row8, -1); /* every slot holds the background everywhere */
 }
 
 __global__ void dbot_free_all_slots_kernel(int32_t* free_stack, int32_t* free_count, int n_phys)
@@ -686,7 +687,8 @@ extern "C" int dbot_b200_reset(dbot_b200_sensor* s)
     dbot_fill_kernel<<<s->num_sms * 8, 256, 0, s->stream>>>(s->d_pool, (size_t)n_phys * s->kp.slot_stride,
                                                             (float)s->background);
     dbot_reset_slots_kernel<<<(n_phys + 255) / 256, 256, 0, s->stream>>>(s->d_loc[0], s->d_free, s->d_free_count,
-                                                                         s->d_slot_rows, n_phys, s->kp.rows);
+                                                                         s->d_slot_rect, n_phys, s->kp.rows,
+                                                                         s->kp.pitch >> 3);
     s->launches += 2;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -874,7 +876,7 @@ static int launch_particles(dbot_b200_sensor* s, const float* d_poses, int32_t* 
     kp.plan = s->d_plan;
     kp.order = s->d_order;
     kp.pending = s->d_pending;
-    kp.slot_rows = s->d_slot_rows;
+    kp.slot_rect = s->d_slot_rect;
     kp.background = (float)s->background;
     kp.poses = d_poses;
     kp.indices = d_indices;
@@ -1118,7 +1120,7 @@ __global__ void dbot_export_slot_kernel(const float* __restrict__ pool, const in
         out[i] = src[i];
 }
 __global__ void dbot_import_pop_kernel(int32_t* loc, int32_t* free_stack, int32_t* free_count, int slot,
-                                       int* err_flag, int2* slot_rows, int rows)
+                                       int* err_flag, int4* slot_rect, int rows, int row8)
 {
     const int f = *free_count;
     if (f <= 0)
@@ -1128,7 +1130,7 @@ __global__ void dbot_import_pop_kernel(int32_t* loc, int32_t* free_stack, int32_
         return;
     }
     loc[slot] = free_stack[f - 1];
-    slot_rows[free_stack[f - 1]] = make_int2(0, rows - 1); /* an imported image may differ from the background anywhere */
+    slot_rect[free_stack[f - 1]] = make_int4(0, rows - 1, 0, row8 - 1); /* an imported image may differ from the background anywhere */
     *free_count = f - 1;
 }
 __global__ void dbot_import_copy_kernel(float* __restrict__ pool, const int32_t* __restrict__ loc, int slot,
@@ -1166,7 +1168,7 @@ extern "C" int dbot_b200_import_slot_device(dbot_b200_sensor* s, const float* d_
     CUDA_TRY(cudaSetDevice(s->device));
     const int slot = s->n_slots;
     dbot_import_pop_kernel<<<1, 1, 0, s->stream>>>(s->d_loc[s->cur], s->d_free, s->d_free_count, slot, s->d_err,
-                                                   s->d_slot_rows, s->kp.rows);
+                                                   s->d_slot_rect, s->kp.rows, s->kp.pitch >> 3);
     dbot_import_copy_kernel<<<64, 256, 0, s->stream>>>(s->d_pool, s->d_loc[s->cur], slot, s->kp.slot_stride, d_src);
     s->launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -1175,26 +1177,41 @@ extern "C" int dbot_b200_import_slot_device(dbot_b200_sensor* s, const float* d_
     return 0;
 }
 
-/* first / last image row of a slot that may differ from the background (first > last: none) */
-extern "C" int dbot_b200_slot_rows(dbot_b200_sensor* s, int32_t slot, int32_t* out_first, int32_t* out_last)
+/* rectangle of a slot that may differ from the background: { first row, last row, first column, last column },
+ * first > last: none */
+extern "C" int dbot_b200_slot_rect(dbot_b200_sensor* s, int32_t slot, int32_t* out_rect)
 {
-    if (!s || !out_first || !out_last) return fail(-1, "slot_rows: null argument");
+    if (!s || !out_rect) return fail(-1, "slot_rect: null argument");
     if (s->multi)
     {
-        if (slot < 0 || slot >= multi_n_slots(s)) return fail(-7, "slot_rows: slot %d of %d", slot, multi_n_slots(s));
+        if (slot < 0 || slot >= multi_n_slots(s)) return fail(-7, "slot_rect: slot %d of %d", slot, multi_n_slots(s));
         int32_t local = 0;
         dbot_b200_sensor* owner = multi_owner(s, slot, &local);
-        return dbot_b200_slot_rows(owner, local, out_first, out_last);
+        return dbot_b200_slot_rect(owner, local, out_rect);
     }
-    if (slot < 0 || slot >= s->n_slots) return fail(-7, "slot_rows: slot %d of %d", slot, s->n_slots);
+    if (slot < 0 || slot >= s->n_slots) return fail(-7, "slot_rect: slot %d of %d", slot, s->n_slots);
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     int32_t phys = 0;
-    int2 r;
+    int4 r;
     CUDA_TRY(cudaMemcpy(&phys, s->d_loc[s->cur] + slot, sizeof(int32_t), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(&r, s->d_slot_rows + phys, sizeof(int2), cudaMemcpyDeviceToHost));
-    *out_first = r.x;
-    *out_last = r.y;
+    CUDA_TRY(cudaMemcpy(&r, s->d_slot_rect + phys, sizeof(int4), cudaMemcpyDeviceToHost));
+    out_rect[0] = r.x;
+    out_rect[1] = r.y;
+    /* columns are kept in 256-bit words (8 floats): the copy's unit */
+    out_rect[2] = r.z <= r.w ? std::min(r.z * 8, s->kp.cols) : s->kp.cols;
+    out_rect[3] = r.z <= r.w ? std::min(r.w * 8 + 7, s->kp.cols - 1) : -1;
+    return 0;
+}
+/* first / last image row of that rectangle */
+extern "C" int dbot_b200_slot_rows(dbot_b200_sensor* s, int32_t slot, int32_t* out_first, int32_t* out_last)
+{
+    if (!out_first || !out_last) return fail(-1, "slot_rows: null argument");
+    int32_t r[4];
+    const int rc = dbot_b200_slot_rect(s, slot, r);
+    if (rc) return rc;
+    *out_first = r[0];
+    *out_last = r[1];
     return 0;
 }
 

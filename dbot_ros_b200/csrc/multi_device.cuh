@@ -117,7 +117,7 @@ static void multi_for_each_shard(dbot_multi* m, F fn)
 
 /* pop n_mig free physical slots for the logical slots first .. first + n_mig - 1 */
 __global__ void dbot_import_pop_many_kernel(int32_t* loc, const int32_t* free_stack, int32_t* free_count, int first,
-                                            int n_mig, int* err_flag, int2* slot_rows, int rows)
+                                            int n_mig, int* err_flag, int4* slot_rect, int rows, int row8)
 {
     const int f = *free_count;
     if (f < n_mig)
@@ -129,7 +129,7 @@ __global__ void dbot_import_pop_many_kernel(int32_t* loc, const int32_t* free_st
     for (int k = threadIdx.x; k < n_mig; k += blockDim.x)
     {
         loc[first + k] = free_stack[f - 1 - k];
-        slot_rows[free_stack[f - 1 - k]] = make_int2(0, rows - 1); /* imported: may differ from the background anywhere */
+        slot_rect[free_stack[f - 1 - k]] = make_int4(0, rows - 1, 0, row8 - 1); /* imported: may differ from the background anywhere */
     }
     __syncthreads();
     if (threadIdx.x == 0) *free_count = f - n_mig;
@@ -467,7 +467,8 @@ static int multi_localise_parents(dbot_b200_sensor* s, const int32_t* indices, i
             CUDA_TRY(cudaMemcpyAsync(m->d_mig[g], m->h_mig[g], (size_t)n_mig * sizeof(dbot_mig_desc),
                                      cudaMemcpyHostToDevice, c->stream));
             dbot_import_pop_many_kernel<<<1, 256, 0, c->stream>>>(c->d_loc[c->cur], c->d_free, c->d_free_count,
-                                                                  c->n_slots, n_mig, c->d_err, c->d_slot_rows, c->kp.rows);
+                                                                  c->n_slots, n_mig, c->d_err, c->d_slot_rect, c->kp.rows,
+                                                                  c->kp.pitch >> 3);
             dbot_import_peer_kernel<<<dim3(16, n_mig), 256, 0, c->stream>>>(c->d_pool, c->d_loc[c->cur], c->n_slots,
                                                                            c->kp.slot_stride, m->d_mig[g]);
             c->launches += 2;

@@ -310,53 +310,67 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
     {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DBOT_STREAM_REGS));
         const int sl = tid - DBOT_CT;
-        const size_t row8 = (size_t)p.pitch >> 3; /* 256-bit words per image row */
-        /* Only the rows in which the parent's image can differ from the background are copied
-         * (dbot_kparams::slot_rows): every image is the background value outside its recorded rows, the
-         * recycled destination slot included -- whose own old rows are first put back to the background
-         * where the parent's rows do not cover them.  A tracked object touches a band of the image, not all
-         * of it; when it has wandered over every row this is the dense copy again.
-         * The loads below keep only DBOT_STREAM_UNROLL x 32 B per thread in flight -- far too
-         * little for HBM latency.  One lane therefore runs a TMA prefetch (cp.async.bulk.prefetch.L2)
-         * DBOT_PREFETCH_AHEAD chunks ahead of the loop, across particle boundaries, so that the
-         * loads hit L2. */
-        constexpr int CHUNK8 = DBOT_ST * DBOT_STREAM_UNROLL;       /* 256-bit words per chunk */
-        auto rows_of = [&](int phys, size_t& first8, int& n8) { /* word range holding the slot's recorded rows */
-            const int2 r = p.slot_rows[phys];
-            first8 = r.x <= r.y ? (size_t)r.x * row8 : 0;
-            n8 = r.x <= r.y ? (int)((size_t)(r.y - r.x + 1) * row8) : 0;
-            return r;
+        const int row8 = p.pitch >> 3; /* 256-bit words per image row */
+        /* Only the rectangle in which the parent's image can differ from the background is copied
+         * (dbot_kparams::slot_rect: rows, and columns in 256-bit words): every image is the background value
+         * outside its recorded rectangle, the recycled destination slot included -- whose own old rectangle is
+         * first put back to the background where the parent's does not cover it.  A tracked object touches a
+         * patch of the image, not all of it; when it has wandered everywhere this is the dense copy again.
+         * The copy walks the rectangle as one flat sequence of 256-bit words (row and word back from the flat
+         * index by a multiply-high).  The loads keep only DBOT_STREAM_UNROLL x 32 B per thread in flight -- far
+         * too little for HBM latency -- so the group's first warp runs a TMA prefetch
+         * (cp.async.bulk.prefetch.L2, one row segment per lane) DBOT_PREFETCH_AHEAD chunks ahead of the loop,
+         * across particle boundaries, and the loads hit L2. */
+        constexpr int CHUNK8 = DBOT_ST * DBOT_STREAM_UNROLL; /* 256-bit words per chunk */
+        struct patch /* a rectangle of one slot as a flat word sequence */
+        {
+            const float* base; /* the slot */
+            int r0, w0, nrows, wcols, n8;
+            uint32_t inv; /* floor(2^32 / wcols) + 1 */
         };
-        auto next_copy = [&](int k, int& n8_next) -> const float* { /* source range of this CTA's next copy */
+        auto make_patch = [&](int phys, const int4& r) {
+            patch c;
+            c.base = p.pool + (size_t)phys * p.slot_stride;
+            c.r0 = r.x; c.w0 = r.z;
+            c.nrows = r.x <= r.y ? r.y - r.x + 1 : 0;
+            c.wcols = r.z <= r.w ? r.w - r.z + 1 : 0;
+            if (c.nrows == 0 || c.wcols == 0) c.nrows = c.wcols = 0;
+            c.n8 = c.nrows * c.wcols;
+            c.inv = c.wcols > 1 ? 0xffffffffu / (uint32_t)c.wcols + 1u : 0u;
+            return c;
+        };
+        auto word_of = [&](const patch& c, int q) -> uint32_t { /* flat word q of the patch -> 256-bit word of the slot */
+            const uint32_t row = c.wcols > 1 ? __umulhi((uint32_t)q, c.inv) : (uint32_t)q;
+            const uint32_t w = (uint32_t)q - row * (uint32_t)c.wcols;
+            return (uint32_t)(c.r0 + (int)row) * (uint32_t)row8 + (uint32_t)(c.w0 + (int)w);
+        };
+        auto next_copy = [&](int k) { /* source patch of this CTA's next copy */
             for (k += gridDim.x; k < p.n; k += gridDim.x)
             {
                 const int4 pl = p.plan[p.order[k]];
-                if (pl.x >= 0 && pl.x != pl.y)
-                {
-                    size_t f8;
-                    rows_of(pl.x, f8, n8_next);
-                    return p.pool + (size_t)pl.x * p.slot_stride + (f8 << 3);
-                }
+                if (pl.x >= 0 && pl.x != pl.y) return make_patch(pl.x, p.slot_rect[pl.x]);
             }
-            n8_next = 0;
-            return nullptr;
+            return make_patch(0, make_int4(0, -1, 0, -1));
         };
-        auto prefetch_chunk = [&](const float* src, int n8, int c) {
-            const int q0 = c * CHUNK8;
-            const int nq = min(CHUNK8, n8 - q0);
-            if (nq > 0)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + ((size_t)q0 << 3)),
-                             "r"(nq * 32)
+        auto prefetch_chunk = [&](const patch& c, int chunk) { /* called by the group's first warp */
+            const int q0 = chunk * CHUNK8;
+            if (q0 >= c.n8) return;
+            const int q1 = min(q0 + CHUNK8, c.n8) - 1;
+            const int ra = c.wcols > 1 ? (int)__umulhi((uint32_t)q0, c.inv) : q0;
+            const int rb = c.wcols > 1 ? (int)__umulhi((uint32_t)q1, c.inv) : q1;
+            for (int r = ra + sl; r <= rb; r += 32)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
+                                 c.base + (((size_t)(c.r0 + r) * (size_t)row8 + (size_t)c.w0) << 3)),
+                             "r"(c.wcols * 32)
                              : "memory");
         };
-        auto fill_rows = [&](float* slot, int ra, int rb) { /* rows [ra, rb] of a slot <- background */
-            if (ra > rb) return;
+        auto fill_rect = [&](float* slot, int ra, int rb, int wa, int wb) { /* rows x words of a slot <- background */
+            if (ra > rb || wa > wb) return;
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = p.background;
-            float* dst = slot + (((size_t)ra * row8) << 3);
-            const int n8 = (int)((size_t)(rb - ra + 1) * row8);
-            for (int q = sl; q < n8; q += DBOT_ST) stg256_stream(dst + ((size_t)q << 3), v);
+            const patch c = make_patch(0, make_int4(ra, rb, wa, wb));
+            for (int q = sl; q < c.n8; q += DBOT_ST) stg256_stream(slot + ((size_t)word_of(c, q) << 3), v);
         };
         bool first = true;
         int done = 0;
@@ -366,61 +380,62 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
             if (pl.x < 0) continue;
             if (pl.x != pl.y)
             {
-                size_t f8;
-                int n8;
-                const int2 pr = rows_of(pl.x, f8, n8);
-                const int2 dr = p.slot_rows[pl.y];
-                const float* in = p.pool + (size_t)pl.x * p.slot_stride + (f8 << 3);
+                const int4 pr = p.slot_rect[pl.x];
+                const int4 dr = p.slot_rect[pl.y];
+                const patch src = make_patch(pl.x, pr);
                 float* slot = p.pool + (size_t)pl.y * p.slot_stride;
-                float* out = slot + (f8 << 3);
-                const int n_chunks = (n8 + CHUNK8 - 1) / CHUNK8;
-                const float* in_next = nullptr;
-                int n8_next = 0;
-                if (sl == 0)
+                const int n_chunks = (src.n8 + CHUNK8 - 1) / CHUNK8;
+                patch nxt = make_patch(0, make_int4(0, -1, 0, -1));
+                if (sl < 32)
                 {
-                    in_next = next_copy(k, n8_next);
+                    nxt = next_copy(k);
                     if (first)
-                        for (int c = 0; c < DBOT_PREFETCH_AHEAD; ++c) prefetch_chunk(in, n8, c);
+                        for (int c = 0; c < DBOT_PREFETCH_AHEAD; ++c) prefetch_chunk(src, c);
                 }
                 first = false;
-                /* what the recycled slot held outside the parent's rows */
-                if (pr.x <= pr.y)
+                /* what the recycled slot held outside the parent's rectangle */
+                if (src.n8 > 0)
                 {
-                    fill_rows(slot, dr.x, min(dr.y, pr.x - 1));
-                    fill_rows(slot, max(dr.x, pr.y + 1), dr.y);
+                    fill_rect(slot, dr.x, min(dr.y, pr.x - 1), dr.z, dr.w);                      /* rows above */
+                    fill_rect(slot, max(dr.x, pr.y + 1), dr.y, dr.z, dr.w);                      /* rows below */
+                    fill_rect(slot, max(dr.x, pr.x), min(dr.y, pr.y), dr.z, min(dr.w, pr.z - 1)); /* left of it */
+                    fill_rect(slot, max(dr.x, pr.x), min(dr.y, pr.y), max(dr.z, pr.w + 1), dr.w); /* right of it */
                 }
                 else
-                    fill_rows(slot, dr.x, dr.y);
+                    fill_rect(slot, dr.x, dr.y, dr.z, dr.w);
                 for (int c = 0; c < n_chunks; ++c)
                 {
-                    if (sl == 0)
+                    if (sl < 32)
                     {
                         const int cp = c + DBOT_PREFETCH_AHEAD;
                         if (cp < n_chunks)
-                            prefetch_chunk(in, n8, cp);
-                        else if (in_next)
-                            prefetch_chunk(in_next, n8_next, cp - n_chunks);
+                            prefetch_chunk(src, cp);
+                        else
+                            prefetch_chunk(nxt, cp - n_chunks);
                     }
                     const int base = c * CHUNK8 + sl;
                     float v[DBOT_STREAM_UNROLL][8];
+                    uint32_t off[DBOT_STREAM_UNROLL];
 #pragma unroll
                     for (int u = 0; u < DBOT_STREAM_UNROLL; ++u)
                     {
                         const int q = base + u * DBOT_ST;
-                        if (q < n8) ldg256(in + ((size_t)q << 3), v[u]);
+                        off[u] = word_of(src, min(q, src.n8 - 1));
+                        if (q < src.n8) ldg256(src.base + ((size_t)off[u] << 3), v[u]);
                     }
 #pragma unroll
                     for (int u = 0; u < DBOT_STREAM_UNROLL; ++u)
                     {
                         const int q = base + u * DBOT_ST;
-                        if (q < n8) stg256_stream(out + ((size_t)q << 3), v[u]);
+                        if (q < src.n8) stg256_stream(slot + ((size_t)off[u] << 3), v[u]);
                     }
                 }
                 __threadfence(); /* this thread's part of the copy is visible device-wide */
                 stream_sync();   /* ... and so is everybody else's */
                 if (sl == 0)
                 {
-                    p.slot_rows[pl.y] = pr;         /* the child's image differs from the background where the parent's does */
+                    /* the child's image differs from the background where the parent's does */
+                    p.slot_rect[pl.y] = src.n8 > 0 ? pr : make_int4(p.rows, -1, row8, -1);
                     atomicSub(p.pending + pl.z, 1); /* one reader of the parent's slot less */
                     ++done;
                     asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(&s_copied)), "r"(done)
@@ -835,10 +850,10 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                 if (MODE == DBOT_MODE_UPDATE)
                 {
                     p.indices[i] = i;
-                    if (have_window) /* posteriors were written inside rows [r0, r1] of the slot */
+                    if (have_window) /* posteriors were written inside the window: rows [r0, r1], columns [c0, c1] */
                     {
-                        const int2 cur = p.slot_rows[pl.y];
-                        p.slot_rows[pl.y] = make_int2(min(cur.x, r0), max(cur.y, r1));
+                        const int4 cur = p.slot_rect[pl.y];
+                        p.slot_rect[pl.y] = make_int4(min(cur.x, r0), max(cur.y, r1), min(cur.z, c0 >> 3), max(cur.w, c1 >> 3));
                     }
                 }
             }

@@ -398,6 +398,13 @@ class B200KinectImageModel(RbSensor):
         abi.check(self._lib, self._lib.dbot_b200_slot_rows(self._h, int(slot), C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def slot_rect(self, slot):
+        """(first row, last row, first column, last column) of the rectangle in which the slot's stored image may
+        differ from the background (columns in steps of 8 pixels); only this part of a parent is copied"""
+        r = (C.c_int32 * 4)()
+        abi.check(self._lib, self._lib.dbot_b200_slot_rect(self._h, int(slot), r))
+        return tuple(int(v) for v in r)
+
     @property
     def free_slots(self):
         return self._lib.dbot_b200_free_slot_count(self._h)

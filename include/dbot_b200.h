@@ -198,6 +198,9 @@ double dbot_b200_observation_time(dbot_b200_sensor* s);
 /* first and last image row in which a slot's stored image may differ from the background value (first > last:
  * nowhere).  An update copies only these rows of a parent to a child that does not adopt its slot. */
 int dbot_b200_slot_rows(dbot_b200_sensor* s, int32_t slot, int32_t* out_first, int32_t* out_last);
+/* the same with columns: out_rect[4] = { first row, last row, first column, last column } (columns in steps of 8
+ * pixels, the copy's 256-bit unit); only this rectangle of a parent is copied */
+int dbot_b200_slot_rect(dbot_b200_sensor* s, int32_t slot, int32_t* out_rect);
 /* physical occlusion slots not in use (pool of 2*max_particles; n_slots + free == pool size) */
 int dbot_b200_free_slot_count(dbot_b200_sensor* s);
 /* occlusion probability image of one slot as of the current observation time, rows*cols floats */

@@ -407,17 +407,17 @@ def test_maximum_sizes_and_ragged_inputs():
 
 
 def test_updates_copy_only_touched_rows_and_images_stay_exact():
-    """An update copies only the rows of the parent's image that an ancestor has ever written
-    (dbot_b200_slot_rows); everything else must already be the background in the recycled destination slot.
-    Two groups of particles track objects at different heights; resampling moves children between the groups,
-    so slots recycled from the tall band are reused under parents with the short band and the other way round.
-    Every occlusion image is compared with the oracle in full, frame after frame."""
+    """An update copies only the rectangle of the parent's image that an ancestor has ever written
+    (dbot_b200_slot_rect); everything else must already be the background in the recycled destination slot.
+    Two groups of particles track objects at different heights and in different columns; resampling moves
+    children between the groups, so slots recycled from one patch are reused under parents with the other patch
+    and the other way round.  Every occlusion image is compared with the oracle in full, frame after frame."""
     n = 40
     sensor, orc, rows, cols, _ = make_pair("ico80", 4, n)
     rng = np.random.default_rng(21)
     assert sensor.slot_rows(0) == (rows, -1)                      # reset: background everywhere
-    top = [(np.eye(3), np.array([0.0, -0.12, 0.8]))]
-    low = [(np.eye(3), np.array([0.05, 0.14, 0.9]))]
+    top = [(np.eye(3), np.array([-0.15, -0.12, 0.8]))]
+    low = [(np.eye(3), np.array([0.17, 0.14, 0.9]))]
     idx = np.zeros(n, dtype=np.int32)
     for f in range(6):
         frame = synth.make_frame(orc.render, top if f % 2 == 0 else low, rows, cols, rng)
@@ -438,11 +438,23 @@ def test_updates_copy_only_touched_rows_and_images_stay_exact():
             assert np.max(np.abs(sensor.occlusion(slot) - orc.occlusion(slot))) < OCC_TOL, (f, slot)
         a, b = sensor.slot_rows(0)
         assert 0 <= a <= b < rows
-    # the bands stayed bands: the upper object never touched the bottom rows and vice versa
-    spans = [sensor.slot_rows(s) for s in range(n)]
-    assert max(b - a + 1 for a, b in spans) < rows
+        r0, r1, c0, c1 = sensor.slot_rect(0)
+        assert (r0, r1) == (a, b) and 0 <= c0 <= c1 < cols and c0 % 8 == 0
+        if f == 0:
+            # after the first update a slot's rectangle is its particle's window, rounded to 8 columns
+            img = np.isfinite(sensor.render(poses[0]))
+            rr, cc = np.nonzero(img)
+            # (the window is the box of the projected vertices: it may exceed the covered pixels by one or two)
+            assert r0 <= rr.min() <= r0 + 2 and r1 - 2 <= rr.max() <= r1
+            assert c0 <= cc.min() < c0 + 10 and c1 - 10 < cc.max() <= c1
+    # the patches stayed patches: the upper object never touched the bottom rows and vice versa, and nobody
+    # the full width
+    spans = [sensor.slot_rect(s) for s in range(n)]
+    assert max(r1 - r0 + 1 for r0, r1, _, _ in spans) < rows
+    assert max(c1 - c0 + 1 for _, _, c0, c1 in spans) < cols
     sensor.reset()
     assert sensor.slot_rows(0) == (rows, -1)
+    assert sensor.slot_rect(0) == (rows, -1, cols, -1)
 
 
 def test_tall_and_wide_triangles_close_to_the_camera():
