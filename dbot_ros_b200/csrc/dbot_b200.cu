@@ -155,6 +155,7 @@ struct dbot_b200_sensor
     cudaStream_t stream;
     dbot_kparams kp; /* template: per-call fields are filled at launch */
     int grid_max, smem_bytes, num_sms;
+    int plan_smem_max; /* dynamic shared memory the update-planning kernel may use for its tables */
     int cull_signs[DBOT_B200_MAX_OBJECTS];
     /* model constants */
     double lambda, wD, c, log_c;
@@ -171,15 +172,15 @@ struct dbot_b200_sensor
     int4* d_slot_rect;      /* touched rectangle of every physical slot */
     double background;      /* stored value of untouched pixels */
     int4* d_plan;
-    float* d_poses;
-    int32_t* d_indices;
+    float* d_poses;         /* poses of a host call and, behind them, its parent indices */
     double* d_out;
+    double* d_result;       /* { error flag (in the first word), log-weights }: one copy back per call */
     float* d_depth;
     int* d_err;
     /* pinned staging */
     float* h_poses;
-    int32_t* h_indices;
     double* h_out;
+    double* h_result;
     float* h_obs;
     float* h_depth;
     int* h_err;
@@ -432,10 +433,10 @@ extern "C" int dbot_b200_destroy(dbot_b200_sensor* s)
     cudaFree(s->d_mesh); cudaFree(s->d_chunks); cudaFree(s->d_obs); cudaFree(s->d_tab);
     cudaFree(s->d_pool); cudaFree(s->d_loc[0]); cudaFree(s->d_loc[1]); cudaFree(s->d_free);
     cudaFree(s->d_free_count); cudaFree(s->d_cnt); cudaFree(s->d_last); cudaFree(s->d_pending);
-    cudaFree(s->d_order); cudaFree(s->d_plan); cudaFree(s->d_slot_rect); cudaFree(s->d_poses); cudaFree(s->d_indices);
-    cudaFree(s->d_out); cudaFree(s->d_depth); cudaFree(s->d_err);
-    cudaFreeHost(s->h_poses); cudaFreeHost(s->h_indices); cudaFreeHost(s->h_out);
-    cudaFreeHost(s->h_obs); cudaFreeHost(s->h_depth); cudaFreeHost(s->h_err);
+    cudaFree(s->d_order); cudaFree(s->d_plan); cudaFree(s->d_slot_rect); cudaFree(s->d_poses);
+    cudaFree(s->d_result); cudaFree(s->d_depth);
+    cudaFreeHost(s->h_poses); cudaFreeHost(s->h_result);
+    cudaFreeHost(s->h_obs); cudaFreeHost(s->h_depth);
     if (s->ev_begin) cudaEventDestroy(s->ev_begin);
     if (s->ev_end) cudaEventDestroy(s->ev_end);
     if (s->ev_k0) cudaEventDestroy(s->ev_k0);
@@ -549,6 +550,9 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     kp.wcap = ((uint32_t)(smem_max - (int)off) / 16u) * 4u; /* pixels, multiple of 4 */
     for (const void* k : kernels)
         CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
+    s->plan_smem_max = (int)prop.sharedMemPerBlockOptin - 4096;
+    CUDA_TRY(cudaFuncSetAttribute((const void*)dbot_plan_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  s->plan_smem_max));
     s->grid_max = s->num_sms; /* one persistent CTA per SM (launch bounds: 1 CTA/SM) */
 
     /* buffers */
@@ -568,20 +572,24 @@ static int create_impl(const dbot_b200_config* cfg, dbot_b200_sensor* s)
     CUDA_TRY(cudaMalloc(&s->d_order, np * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&s->d_slot_rect, 2 * np * sizeof(int4)));
     CUDA_TRY(cudaMalloc(&s->d_plan, np * sizeof(int4)));
-    CUDA_TRY(cudaMalloc(&s->d_poses, np * 12 * kp.n_obj * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&s->d_indices, np * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&s->d_out, np * sizeof(double)));
+    /* per-call traffic of the host entry points, packed so that each direction is ONE copy: poses and parent
+     * indices of a call go up back to back; the error flag sits in front of the log-weights and comes back with
+     * them */
+    CUDA_TRY(cudaMalloc(&s->d_poses, np * 12 * kp.n_obj * sizeof(float) + np * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_result, (np + 1) * sizeof(double)));
+    CUDA_TRY(cudaMemset(s->d_result, 0, sizeof(double)));
+    s->d_err = (int*)s->d_result;
+    s->d_out = s->d_result + 1;
     CUDA_TRY(cudaMalloc(&s->d_depth, P * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&s->d_err, sizeof(int)));
-    CUDA_TRY(cudaMemset(s->d_err, 0, sizeof(int)));
     s->device_bytes += (int64_t)(2 * P * sizeof(float) + kp.slot_stride * sizeof(float4) +
                                  2 * state_bytes + np * (12 * kp.n_obj * 4 + 4 + 8 + 8 * 4 + 16) + 8);
-    CUDA_TRY(cudaHostAlloc(&s->h_poses, np * 12 * kp.n_obj * sizeof(float), cudaHostAllocDefault));
-    CUDA_TRY(cudaHostAlloc(&s->h_indices, np * sizeof(int32_t), cudaHostAllocDefault));
-    CUDA_TRY(cudaHostAlloc(&s->h_out, np * sizeof(double), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&s->h_poses, np * 12 * kp.n_obj * sizeof(float) + np * sizeof(int32_t), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&s->h_result, (np + 1) * sizeof(double), cudaHostAllocDefault));
+    s->h_err = (int*)s->h_result;
+    s->h_out = s->h_result + 1;
+    *s->h_err = 0;
     CUDA_TRY(cudaHostAlloc(&s->h_obs, P * sizeof(float), cudaHostAllocDefault));
     CUDA_TRY(cudaHostAlloc(&s->h_depth, P * sizeof(float), cudaHostAllocDefault));
-    CUDA_TRY(cudaHostAlloc(&s->h_err, sizeof(int), cudaHostAllocDefault));
     /* until the first set_observation every pixel is "no data" */
     CUDA_TRY(cudaMemsetAsync(s->d_obs, 0xff, P * sizeof(float), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->d_tab, 0xff, kp.slot_stride * sizeof(float4), s->stream));
@@ -889,9 +897,11 @@ static int launch_particles(dbot_b200_sensor* s, const float* d_poses, int32_t* 
     if (update)
     {
         prof_begin(s);
-        dbot_plan_update_kernel<<<1, DBOT_PLAN_THREADS, 0, s->stream>>>(
+        const size_t table_bytes = (size_t)s->n_slots * 2 * sizeof(int32_t);
+        const int in_smem = table_bytes <= (size_t)s->plan_smem_max;
+        dbot_plan_update_kernel<<<1, DBOT_PLAN_THREADS, in_smem ? table_bytes : 0, s->stream>>>(
             d_indices, n, s->n_slots, s->d_loc[s->cur], s->d_loc[s->cur ^ 1], s->d_free, s->d_free_count,
-            s->d_cnt, s->d_last, s->d_pending, s->d_order, s->d_plan, s->d_err);
+            s->d_cnt, s->d_last, s->d_pending, s->d_order, s->d_plan, s->d_err, in_smem);
         CUDA_TRY(cudaGetLastError());
         prof_end(s, DBOT_B200_KERNEL_PLAN);
     }
@@ -959,26 +969,36 @@ static int empty_update(dbot_b200_sensor* s)
     return 0;
 }
 
+/* poses and parent indices of one call: staged back to back in page-locked memory, one copy up */
+static int stage_call_inputs(dbot_b200_sensor* s, const float* poses, const int32_t* indices, int32_t n,
+                             int32_t** d_indices)
+{
+    const size_t pose_floats = (size_t)n * 12 * s->kp.n_obj;
+    memcpy(s->h_poses, poses, pose_floats * sizeof(float));
+    memcpy(s->h_poses + pose_floats, indices, (size_t)n * sizeof(int32_t));
+    CUDA_TRY(cudaMemcpyAsync(s->d_poses, s->h_poses, pose_floats * sizeof(float) + (size_t)n * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, s->stream));
+    *d_indices = (int32_t*)(s->d_poses + pose_floats);
+    return 0;
+}
+
 /* first half of RbSensor::loglikes: stage the host arrays, enqueue copies and kernels, no wait */
 static int loglikes_enqueue(dbot_b200_sensor* s, const float* poses, const int32_t* indices, int32_t n,
                             int32_t update)
 {
     CUDA_TRY(cudaSetDevice(s->device));
-    const size_t pose_bytes = (size_t)n * 12 * s->kp.n_obj * sizeof(float);
-    memcpy(s->h_poses, poses, pose_bytes);
-    memcpy(s->h_indices, indices, (size_t)n * sizeof(int32_t));
-    CUDA_TRY(cudaMemcpyAsync(s->d_poses, s->h_poses, pose_bytes, cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(s->d_indices, s->h_indices, (size_t)n * sizeof(int32_t),
-                             cudaMemcpyHostToDevice, s->stream));
-    return launch_particles(s, s->d_poses, s->d_indices, n, update, s->d_out);
+    int32_t* d_indices = nullptr;
+    int rc = stage_call_inputs(s, poses, indices, n, &d_indices);
+    if (rc) return rc;
+    return launch_particles(s, s->d_poses, d_indices, n, update, s->d_out);
 }
 /* second half: log-weights and the error flag back, wait, report */
 static int loglikes_finish(dbot_b200_sensor* s, int32_t n, int32_t update, double* out_loglikes)
 {
     CUDA_TRY(cudaSetDevice(s->device));
-    if (n > 0 && out_loglikes)
-        CUDA_TRY(cudaMemcpyAsync(s->h_out, s->d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(s->h_err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    /* the error flag and, behind it, the log-weights: one copy */
+    const size_t back = (n > 0 && out_loglikes) ? (size_t)(n + 1) * sizeof(double) : sizeof(int);
+    CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_result, back, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     int rc = device_error(s, "loglikes", update);
     if (rc) return rc;

@@ -218,16 +218,10 @@ extern "C" int dbot_b200_loglikes_gather(dbot_b200_sensor* s, const float* poses
                         indices_local[i], s->n_slots);
     CUDA_TRY(cudaSetDevice(s->device));
     const double ht0 = s->host_timing ? host_now_us() : 0.0;
-    if (n_local > 0)
-    {
-        const size_t pose_bytes = (size_t)n_local * 12 * s->kp.n_obj * sizeof(float);
-        memcpy(s->h_poses, poses_local, pose_bytes);
-        memcpy(s->h_indices, indices_local, (size_t)n_local * sizeof(int32_t));
-        CUDA_TRY(cudaMemcpyAsync(s->d_poses, s->h_poses, pose_bytes, cudaMemcpyHostToDevice, s->stream));
-        CUDA_TRY(cudaMemcpyAsync(s->d_indices, s->h_indices, (size_t)n_local * sizeof(int32_t), cudaMemcpyHostToDevice,
-                                 s->stream));
-    }
-    int rc = peer_gather_enqueue(s, s->d_poses, s->d_indices, n_local, update, s->d_out, width);
+    int32_t* d_indices = nullptr;
+    int rc = n_local > 0 ? stage_call_inputs(s, poses_local, indices_local, n_local, &d_indices) : 0;
+    if (rc) return rc;
+    rc = peer_gather_enqueue(s, s->d_poses, d_indices, n_local, update, s->d_out, width);
     if (rc) return rc;
     const size_t bytes = (size_t)pg->world * width * sizeof(double);
     CUDA_TRY(cudaMemcpyAsync(pg->h_all, dbot_b200_peer_gather_result(s), bytes, cudaMemcpyDeviceToHost, s->stream));

@@ -98,12 +98,20 @@ __global__ void __launch_bounds__(DBOT_PLAN_THREADS, 1)
     dbot_plan_update_kernel(const int32_t* __restrict__ parents, int n, int n_slots,
                             const int32_t* __restrict__ loc, int32_t* __restrict__ loc_next,
                             int32_t* __restrict__ free_stack, int32_t* __restrict__ free_count,
-                            int32_t* __restrict__ cnt, int32_t* __restrict__ last,
+                            int32_t* cnt, int32_t* last,
                             int32_t* __restrict__ pending, int32_t* __restrict__ order,
-                            int4* __restrict__ plan, int* __restrict__ err_flag)
+                            int4* __restrict__ plan, int* __restrict__ err_flag, int tables_in_smem)
 {
     __shared__ int s_warp[33];
+    extern __shared__ int32_t s_tables[];
     const int t = threadIdx.x;
+    /* children per parent and each parent's last child: in shared memory when they fit (the kernel is a chain of
+     * dependent look-ups by one CTA; with the two tables in global memory it takes 11 us for 1000 particles) */
+    if (tables_in_smem)
+    {
+        cnt = s_tables;
+        last = s_tables + n_slots;
+    }
     for (int sidx = t; sidx < n_slots; sidx += DBOT_PLAN_THREADS)
     {
         cnt[sidx] = 0;
