@@ -436,6 +436,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                 {
                     /* the child's image differs from the background where the parent's does */
                     p.slot_rect[pl.y] = src.n8 > 0 ? pr : make_int4(p.rows, -1, row8, -1);
+                    __threadfence(); /* in L2 before this particle's compute warps reduce their window into it */
                     atomicSub(p.pending + pl.z, 1); /* one reader of the parent's slot less */
                     ++done;
                     asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(&s_copied)), "r"(done)
@@ -852,8 +853,11 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                     p.indices[i] = i;
                     if (have_window) /* posteriors were written inside the window: rows [r0, r1], columns [c0, c1] */
                     {
-                        const int4 cur = p.slot_rect[pl.y];
-                        p.slot_rect[pl.y] = make_int4(min(cur.x, r0), max(cur.y, r1), min(cur.z, c0 >> 3), max(cur.w, c1 >> 3));
+                        /* four reductions that nobody waits for (a load + store would hold this warp, and with
+                         * it the next particle's first barrier, for one trip to L2) */
+                        int* rect = reinterpret_cast<int*>(p.slot_rect + pl.y);
+                        atomicMin(rect + 0, r0); atomicMax(rect + 1, r1);
+                        atomicMin(rect + 2, c0 >> 3); atomicMax(rect + 3, c1 >> 3);
                     }
                 }
             }
