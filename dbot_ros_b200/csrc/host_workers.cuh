@@ -38,16 +38,22 @@ struct dbot_shard_worker
                 cv.wait(lk, [&] { return quit || posted.load(std::memory_order_acquire) != seen; });
                 if (quit) return;
             }
-            seen = posted.load(std::memory_order_acquire);
-            job();
+            std::function<void()> run;
+            {
+                /* a copy: post() may hand over the next job while this one is still running */
+                std::lock_guard<std::mutex> lk(mu);
+                run = job;
+                seen = posted.load(std::memory_order_acquire);
+            }
+            run();
             finished.store(seen, std::memory_order_release);
         }
     }
     void post(std::function<void()> j)
     {
-        job = std::move(j);
         {
             std::lock_guard<std::mutex> lk(mu);
+            job = std::move(j);
             posted.fetch_add(1, std::memory_order_release);
         }
         cv.notify_one();
