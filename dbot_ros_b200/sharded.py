@@ -73,7 +73,15 @@ class ShardedRbSensor(RbSensor):
         self.n_slots = 1          # global slot count; after reset every rank holds slot 0
         self._buf = None
         self._out_all = None
+        # the library's one-pass check of a call's parent vector (host code, needs no GPU)
         lib = getattr(local_sensor, "_lib", None)
+        if lib is None:
+            try:
+                from . import abi
+
+                lib = abi.load_library()
+            except (ImportError, OSError):
+                lib = None      # a test double as the local sensor on a machine without the built library
         self._scan = getattr(lib, "dbot_b200_shard_scan", None)
         # parents imported since the last update: for EVERY rank the set of global slots it holds a
         # copy of (all ranks track all sets: the schedule must come out the same everywhere), and for

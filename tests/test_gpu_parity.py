@@ -519,3 +519,38 @@ def test_failed_update_on_the_device_needs_reset():
     with pytest.raises(DbotB200Error):
         sensor.synchronize()
     assert sensor.loglikes_poses(poses, np.arange(n, dtype=np.int32), False).shape == (n,)
+
+
+def test_pageable_frames_staged_with_and_without_helper_threads():
+    """dbot_b200_set_observation stages a pageable VGA frame in pieces that the calling thread and up to two
+    helper threads claim (csrc/host_workers.cuh); page-locked frames are copied as they are.  All three ways must
+    put the same frame on the device: identical log-weights, frame after frame, and bad option values are refused."""
+    import torch
+
+    n = 16
+    sensor, orc, rows, cols, _ = make_pair("ico80", 1, n)
+    rng = np.random.default_rng(33)
+    gt = [(np.eye(3), np.array([0.02, -0.01, 0.7]))]
+    poses = synth.particle_poses(gt, n, rng)
+    frames = [synth.make_frame(orc.render, gt, rows, cols, rng) for _ in range(6)]
+    results = {}
+    for mode in ("helpers", "alone", "pinned"):
+        sensor.reset()
+        sensor.set_staging_threads(0 if mode == "alone" else 2)
+        got = []
+        for f in frames:
+            img = torch.from_numpy(f.copy()).pin_memory().numpy() if mode == "pinned" else f.copy()
+            sensor.set_observation(img)
+            img[:] = np.nan            # the caller may reuse its buffer as soon as the call has returned
+            got.append(sensor.loglikes_poses(poses, np.zeros(n, np.int32) if not got else np.arange(n, dtype=np.int32), True))
+        results[mode] = np.stack(got)
+    assert np.array_equal(results["helpers"], results["alone"])
+    assert np.array_equal(results["helpers"], results["pinned"])
+    orc.reset()
+    want = []
+    for f in frames:
+        orc.set_observation(f)
+        want.append(orc.loglikes_poses(poses, np.zeros(n, np.int32) if not want else np.arange(n, dtype=np.int32), True))
+    assert rel_err(results["helpers"], np.stack(want)) < REL_TOL
+    with pytest.raises(DbotB200Error):
+        sensor.set_staging_threads(7)
