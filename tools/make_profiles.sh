@@ -1,5 +1,5 @@
 #!/bin/bash
-# profiles/ for round 2 from the files a gpurun evidence call left in gpurun_out/ (tools/r2_gpu14.sh)
+# profiles/ for round 2 from the files a gpurun evidence call left in gpurun_out/ (tools/evidence_1gpu.sh)
 # usage: tools/make_profiles.sh <suffix of the evidence run, e.g. 14>
 set -e
 n=$1; o=gpurun_out; p=profiles
