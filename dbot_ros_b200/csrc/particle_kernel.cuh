@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
     __shared__ uint32_t s_mask[DBOT_CW][32];     /* first-row masks of the span batches, per warp */
     __shared__ double s_red[DBOT_CW];
     __shared__ int s_copied;                     /* update: copies this CTA's streaming warps have finished */
+    __shared__ int s_gave_up;                    /* update: a wait for a slot ran into its bound (error 3) */
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
         mbar_init(&s_bar, 1);
         mbar_fence_init();
         s_copied = 0;
+        s_gave_up = 0;
         s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0;
     }
     __syncthreads();
@@ -619,12 +621,13 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
         const int ww = c1 - c0 + 1;
         float acc = 0.0f;
         bool copied = false; /* update: this particle's slot is ready for the posterior */
-        auto await_slot = [&]() {
+        auto await_slot = [&]() -> bool {
             /* a copying child: its slot holds the parent's image once the streaming warps have counted the
              * copy.  An adopting child owns the parent's slot itself and waits until every copy of it has
              * been taken (pending).  Neither wait depends on anything that waits itself, so both end; the
              * bound (about a second) only turns a scheduling accident into an error code instead of a hung
-             * GPU. */
+             * GPU -- and the particle then leaves the slot alone (a sibling may still be reading it): the CTA's
+             * compute warps stop, the call fails with -11 and the handle wants a reset(). */
             if (tid == 0)
             {
                 int spins = 0;
@@ -644,6 +647,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                     if (++spins > (1 << 22))
                     {
                         atomicExch(p.err_flag, 3);
+                        s_gave_up = 1;
                         break;
                     }
                 }
@@ -651,6 +655,7 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
             }
             compute_sync();
             copied = true;
+            return s_gave_up == 0;
         };
 
         if (have_window)
@@ -714,7 +719,13 @@ __global__ void __launch_bounds__(DBOT_CT + (MODE == DBOT_MODE_UPDATE ? DBOT_ST 
                 }
                 compute_sync();
                 if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; } /* every warp has left the sweep */
-                if (MODE == DBOT_MODE_UPDATE && !copied) await_slot();
+                if (MODE == DBOT_MODE_UPDATE && !copied && !await_slot())
+                {
+                    /* the slot never became this particle's (error 3): these warps write no more state in this
+                     * launch.  The streaming warps go on -- other CTAs' adopters wait for their copies only. */
+                    if (tid == 0) p.out[i] = __longlong_as_double(0x7ff8000000000000LL);
+                    return;
+                }
                 /* ---- per-pixel mixture over the band: a warp per row, DBOT_UNIT_PX x 32 columns
                  * (and their loads) in flight per step ---- */
                 if (MODE == DBOT_MODE_RENDER)
