@@ -788,11 +788,14 @@ extern "C" int dbot_b200_set_observation(dbot_b200_sensor* s, const float* depth
     const size_t bytes = (size_t)s->kp.rows * s->kp.cols * sizeof(float);
     if (is_pinned_host(depth_m))
     {
-        /* the caller's buffer is page-locked: copy straight from it, and be done with it on return */
+        /* the caller's buffer is page-locked: copy straight from it, and be done with it on return -- with the
+         * copy, that is; the table kernel is left running like everything else on the stream */
         CUDA_TRY(cudaMemcpyAsync(s->d_obs, depth_m, bytes, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaEventRecord(s->ev_obs, s->stream));
         int rc = launch_observation(s, s->d_obs);
         if (rc) return rc;
-        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        CUDA_TRY(cudaEventSynchronize(s->ev_obs));
+        s->obs_in_flight = 0;
         return 0;
     }
     /* pageable: stage in the handle's own pinned buffer; the copy and the table kernel are left
