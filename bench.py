@@ -37,7 +37,14 @@ from dbot_ros_b200 import CameraData, ObjectModel, Parameters, RbSensorBuilder, 
 
 METRIC = "particle-likelihoods/sec"  # BASELINE.json: "particle-likelihoods/sec & FPS @640x480, 5k-tri mesh, ..." (FPS is the line's "fps" key)
 UNIT = "particle-likelihoods/s"
-CONFIG_ID = 2            # BASELINE.json configs[1]: 1000 particles, 640x480, single 5k-tri mesh
+# BASELINE.json configs[1] (1000 particles, 640x480, single 5k-tri mesh) is the workload the metric is quoted on and
+# what the driver runs.  DBOT_BENCH_CONFIG=3 selects configs[2] (10 000 particles; under torchrun that is configs[3]:
+# 10 000 particles per GPU, 80 000 on eight) for the same line.
+CONFIG_ID = int(os.environ.get("DBOT_BENCH_CONFIG", "2"))
+if CONFIG_ID == 4:
+    CONFIG_ID = 3        # the same per-GPU workload
+if CONFIG_ID not in (2, 3):
+    raise SystemExit("bench.py: DBOT_BENCH_CONFIG must be 2, 3 or 4")
 N_FRAMES = 4             # distinct synthetic frames / pose sets cycled through the steps
 REPEATS = 5              # the K timed steps are run this many times; the median repeat is reported
 
