@@ -7,12 +7,13 @@ particles (ref:source/dbot_ros/object_tracker_ros.hpp:49 -> dbot filter, SURVEY.
 
   value   device-resident: frames, poses and parent indices already in HBM, the two kernels
           launched through the *_device C-ABI entry points, timed with CUDA events on the
-          library's stream.  The K timed steps are repeated REPEATS times; value is the median repeat.
+          library's stream.  The K timed steps are repeated (at least REPEATS times, until a quarter of a second of
+          device time has passed); value is the median repeat.
   e2e     the same step through the reference-facing host call with ordinary (pageable) host numpy
           buffers in and host log-weights out -- what the C++ adapter hands over; H2D/D2H inside the
           timed region.  e2e_pinned: the same from page-locked buffers.
   roofline  the fused particle kernel (update).  achieved = the bytes the launch actually has to move
-          (copying children x 8 B x touched rows x row pitch + covered pixels x 8 B per particle) / launch duration from CUDA
+          (copying children x 8 B x pixels of the parent's touched rectangle + covered pixels x 8 B per particle) / launch duration from CUDA
           events; frac_dram = DRAM bytes ncu counted for the same launch / duration / peak; the
           dense-formulation figure of SURVEY.md 8(d) (8P per particle whether copied or not) is kept
           beside it as dense_equivalent.  `bound` says what ncu shows limits the kernel.
@@ -376,10 +377,15 @@ def main():
     # per-kernel); a few tens of milliseconds of GPU work are too short for one loop alone
     clocks = ClockSampler(local_rank)
     clocks.__enter__()
-    rep_ms = []
-    for _ in range(REPEATS):
+    # the K timed steps are repeated until the device has been under load for a quarter of a second (at least
+    # REPEATS times, at most 100): K = 20 steps of 0.3 ms alone are 6 ms, too short for clocks and caches to
+    # settle and for the driver's sampler to see the GPU busy.  Every repeat times exactly K steps; the median
+    # repeat is reported.  (timed() returns the maximum over ranks, so every rank takes the same decision.)
+    rep_ms = [timed(device_step, args.steps)]
+    n_rep = int(min(100, max(REPEATS, np.ceil(250.0 / max(rep_ms[0], 1e-3)))))
+    while len(rep_ms) < n_rep:
         rep_ms.append(timed(device_step, args.steps))
-    gpu_launches = int(sensor.launch_count - launches0) // REPEATS
+    gpu_launches = int(sensor.launch_count - launches0) // n_rep
     ms = float(np.median(rep_ms))
     value = n * world * args.steps / (ms * 1e-3)
 
@@ -503,7 +509,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": describe(w, world), "fps": args.steps / (ms * 1e-3),
-            "repeats": {"count": REPEATS, "steps_each": args.steps, "ms_per_step": [m / args.steps for m in rep_ms],
+            "repeats": {"count": n_rep, "steps_each": args.steps,
+                        "ms_per_step": [round(m / args.steps, 6) for m in rep_ms],
                         "value_min": n * world * args.steps / (max(rep_ms) * 1e-3),
                         "value_max": n * world * args.steps / (min(rep_ms) * 1e-3), "reported": "median"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
